@@ -1,0 +1,838 @@
+// apm_api.cu -- C-ABI launcher of libapm_b200 (see include/apm_b200.h for the contract and the
+// reference interfaces each entry point replaces).  Host side only: argument checking, the per-call
+// alphabet / Peq tables / pattern groups ("plan"), shard arithmetic, kernel launches.  All arithmetic
+// of the hot path happens in the CUDA kernels (apm_myers.cuh, apm_dp.cuh); there is no CPU fallback.
+#include "../../include/apm_b200.h"
+
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "apm_common.cuh"
+#include "apm_dp.cuh"
+#include "apm_myers.cuh"
+#include "apm_util_kernels.cuh"
+
+using namespace apm;
+
+namespace {
+
+thread_local std::string tl_err;
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    tl_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(APM_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+enum { SHARD_AUTO = 0, SHARD_DB = 1, SHARD_PATTERNS = 2 };
+enum { KERNEL_MYERS = 0, KERNEL_DP = 1 };
+enum { MODE_DIRECT = 0, MODE_FILTER = 1 };
+
+struct Options {
+    int gpus = 1;  // 0 = all
+    int shard = SHARD_AUTO;
+    int kernel = KERNEL_MYERS;
+    int mode = MODE_DIRECT;
+    int rblock = 0;  // 0 = auto
+    int tile = 0;    // 0 = auto
+    long long dp_scratch_mb = 256;
+};
+std::mutex g_opt_mu;
+Options g_opt;
+thread_local std::string tl_optbuf;
+
+Options options_snapshot() {
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    return g_opt;
+}
+
+int device_ready(int *ndev) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(APM_ENODEVICE, "no usable CUDA device (%s); libapm_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    *ndev = n;
+    return APM_OK;
+}
+
+// ---- kernel dispatch table ------------------------------------------------------------------------
+using MyersKernel = void (*)(const MyersArgs);
+template <int NW>
+MyersKernel pick_r(int R) {
+    switch (R) {
+        case 1: return myers_count_kernel<NW, 1>;
+        case 2: return myers_count_kernel<NW, 2>;
+        default: return myers_count_kernel<NW, 4>;
+    }
+}
+MyersKernel pick_kernel(int NW, int R) {
+    switch (NW) {
+        case 1: return pick_r<1>(R);
+        case 2: return pick_r<2>(R);
+        case 3: return pick_r<3>(R);
+        case 4: return pick_r<4>(R);
+        case 5: return pick_r<5>(R);
+        case 6: return pick_r<6>(R);
+        case 7: return pick_r<7>(R);
+        default: return pick_r<8>(R);
+    }
+}
+
+struct Bucket {
+    int NW = 1, R = 1, EW = 1, ngroups = 0, mmax = 0, mmin = 0;
+    std::vector<int> group_m, group_pat;
+    std::vector<uint32_t> peq;
+    uint32_t *d_peq = nullptr;
+    int *d_group_m = nullptr, *d_group_pat = nullptr;
+    MyersKernel fn = nullptr;
+    size_t smem_set = 0;
+    int occ_cache_smem = -1, occ_cache = 0;
+};
+
+template <typename T>
+int upload(T **dptr, const std::vector<T> &h) {
+    *dptr = nullptr;
+    if (h.empty()) return APM_OK;
+    CUDA_TRY(cudaMalloc((void **)dptr, h.size() * sizeof(T)));
+    CUDA_TRY(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return APM_OK;
+}
+
+}  // namespace
+
+struct apm_plan {
+    int device = 0, P = 0, k = 0, ncodes = 0, num_sms = 0, mmax_all_patterns = 0;
+    Options opt;
+    std::vector<std::string> pats;
+    uint8_t code_of[256];
+    int shard_rank = 0, shard_world = 1;
+    std::vector<Bucket> buckets;
+    std::vector<int> tail_list, all_list;
+    int tail_width = 0, tail_mmax = 0, all_mmax = 0;
+    uint8_t *d_code_of = nullptr, *d_pat_bytes = nullptr;
+    long long *d_pat_off = nullptr;
+    int *d_pat_len = nullptr, *d_tail_list = nullptr, *d_all_list = nullptr;
+    unsigned long long *d_counts = nullptr;
+    uint32_t *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+namespace {
+
+void free_work(apm_plan *pl) {
+    for (auto &b : pl->buckets) {
+        cudaFree(b.d_peq);
+        cudaFree(b.d_group_m);
+        cudaFree(b.d_group_pat);
+    }
+    pl->buckets.clear();
+    cudaFree(pl->d_tail_list);
+    cudaFree(pl->d_all_list);
+    pl->d_tail_list = pl->d_all_list = nullptr;
+    pl->tail_list.clear();
+    pl->all_list.clear();
+}
+
+int auto_rblock(int NW) { return NW <= 2 ? 4 : (NW <= 4 ? 2 : 1); }
+
+// (Re)build buckets / DP lists for the active patterns (pattern shard) and upload them.
+int build_work(apm_plan *pl) {
+    free_work(pl);
+    std::vector<std::vector<int>> by_nw(kMaxWords + 1);
+    pl->tail_width = pl->tail_mmax = pl->all_mmax = 0;
+    for (int p = 0; p < pl->P; ++p) {
+        if (p % pl->shard_world != pl->shard_rank) continue;
+        const int m = (int)pl->pats[p].size();
+        if (pl->opt.kernel == KERNEL_DP || m > kMaxMyersLen) {
+            pl->all_list.push_back(p);
+            pl->all_mmax = std::max(pl->all_mmax, m);
+            continue;
+        }
+        by_nw[(m + 31) / 32].push_back(p);
+        const int tw = m - 1 - pl->k;  // number of truncated tail windows (sequential.c:121,131-134)
+        if (tw > 0) {
+            pl->tail_list.push_back(p);
+            pl->tail_width = std::max(pl->tail_width, tw);
+            pl->tail_mmax = std::max(pl->tail_mmax, m);
+        }
+    }
+    for (int NW = 1; NW <= kMaxWords; ++NW) {
+        auto &ids = by_nw[NW];
+        if (ids.empty()) continue;
+        std::stable_sort(ids.begin(), ids.end(),
+                         [&](int a, int b) { return pl->pats[a].size() < pl->pats[b].size(); });
+        Bucket b;
+        b.NW = NW;
+        b.R = pl->opt.rblock ? pl->opt.rblock : auto_rblock(NW);
+        b.EW = entry_words(b.R * NW);
+        b.fn = pick_kernel(NW, b.R);
+        b.mmin = (int)pl->pats[ids.front()].size();
+        b.mmax = (int)pl->pats[ids.back()].size();
+        size_t i = 0;
+        while (i < ids.size()) {
+            const int m = (int)pl->pats[ids[i]].size();
+            b.group_m.push_back(m);
+            for (int r = 0; r < b.R; ++r) {
+                if (i < ids.size() && (int)pl->pats[ids[i]].size() == m) b.group_pat.push_back(ids[i++]);
+                else b.group_pat.push_back(-1);
+            }
+        }
+        b.ngroups = (int)b.group_m.size();
+        b.peq.assign((size_t)b.ngroups * pl->ncodes * b.EW, 0u);
+        for (int g = 0; g < b.ngroups; ++g)
+            for (int r = 0; r < b.R; ++r) {
+                const int p = b.group_pat[(size_t)g * b.R + r];
+                if (p < 0) continue;
+                const std::string &s = pl->pats[p];
+                for (size_t x = 0; x < s.size(); ++x) {
+                    const int c = pl->code_of[(uint8_t)s[x]];
+                    b.peq[((size_t)g * pl->ncodes + c) * b.EW + (size_t)r * NW + (x >> 5)] |= 1u << (x & 31);
+                }
+            }
+        int rc;
+        if ((rc = upload(&b.d_peq, b.peq))) return rc;
+        if ((rc = upload(&b.d_group_m, b.group_m))) return rc;
+        if ((rc = upload(&b.d_group_pat, b.group_pat))) return rc;
+        pl->buckets.push_back(std::move(b));
+    }
+    int rc;
+    if ((rc = upload(&pl->d_tail_list, pl->tail_list))) return rc;
+    if ((rc = upload(&pl->d_all_list, pl->all_list))) return rc;
+    return APM_OK;
+}
+
+int ensure_scratch(apm_plan *pl, size_t bytes) {
+    if (bytes <= pl->scratch_bytes) return APM_OK;
+    if (pl->d_scratch) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaFree(pl->d_scratch));
+        pl->d_scratch = nullptr;
+        pl->scratch_bytes = 0;
+    }
+    CUDA_TRY(cudaMalloc((void **)&pl->d_scratch, bytes));
+    pl->scratch_bytes = bytes;
+    return APM_OK;
+}
+
+int launch_myers(apm_plan *pl, Bucket &b, const uint8_t *d_buf, long long buf_len, long long n_end,
+                 long long w0, long long w1, cudaStream_t st) {
+    // windows of the shortest pattern of the bucket that are full-length
+    const long long lim = std::min(w1, n_end - b.mmin + 1);
+    if (lim <= w0) return APM_OK;
+    const long long nwin = lim - w0;  // longer patterns have fewer full windows; the kernel clips per group
+
+    // ---- launch geometry -----------------------------------------------------------------------
+    const size_t per_group = (size_t)pl->ncodes * b.EW * 4 + (size_t)(1 + 2 * b.R) * 4;
+    const size_t budget = 48 * 1024;
+    int gpc_max = (int)std::max<size_t>(1, budget / per_group);
+    int tile = pl->opt.tile ? pl->opt.tile : 1024;
+    const int cap_guess = pl->num_sms * 4;
+    while (!pl->opt.tile && tile > kThreads && (nwin + tile - 1) / tile < cap_guess) tile /= 2;
+    long long ntiles = (nwin + tile - 1) / tile;
+
+    int gpc = std::min(b.ngroups, gpc_max);
+    size_t smem = myers_smem_bytes(tile, b.mmax, gpc, pl->ncodes, b.R, b.NW);
+    if (smem > b.smem_set) {
+        CUDA_TRY(cudaFuncSetAttribute(b.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        b.smem_set = smem;
+    }
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, b.fn, kThreads, smem));
+    if (occ < 1) return fail(APM_ECUDA, "myers kernel NW=%d R=%d does not fit an SM (smem %zu)", b.NW, b.R, smem);
+    const long long capacity = (long long)pl->num_sms * occ;
+    unsigned gx, gy = 1;
+    if (ntiles >= capacity) {
+        gx = (unsigned)capacity;
+    } else {
+        gx = (unsigned)ntiles;
+        long long want_y = std::min<long long>(b.ngroups, (capacity + ntiles - 1) / ntiles);
+        gpc = std::min(gpc, (int)((b.ngroups + want_y - 1) / want_y));
+        const int nchunks = (b.ngroups + gpc - 1) / gpc;
+        gy = (unsigned)std::min<long long>(want_y, nchunks);
+        smem = myers_smem_bytes(tile, b.mmax, gpc, pl->ncodes, b.R, b.NW);
+    }
+
+    MyersArgs a;
+    a.buf = d_buf;
+    a.buf_len = buf_len;
+    a.n_end = n_end;
+    a.w0 = w0;
+    a.w1 = lim;
+    a.peq = b.d_peq;
+    a.group_m = b.d_group_m;
+    a.group_pat = b.d_group_pat;
+    a.code_of = pl->d_code_of;
+    a.counts = pl->d_counts;
+    a.ngroups = b.ngroups;
+    a.ncodes = pl->ncodes;
+    a.groups_per_chunk = gpc;
+    a.mmax = b.mmax;
+    a.k = pl->k;
+    a.tile = tile;
+    b.fn<<<dim3(gx, gy), kThreads, smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    g_launches++;
+    return APM_OK;
+}
+
+int launch_dp(apm_plan *pl, const uint8_t *d_buf, long long buf_offset, long long n_total, long long j_begin,
+              long long j_end, cudaStream_t st) {
+    const size_t budget = (size_t)pl->opt.dp_scratch_mb << 20;
+    DpArgs a;
+    a.buf = d_buf;
+    a.buf_offset = buf_offset;
+    a.n_total = n_total;
+    a.j_begin = j_begin;
+    a.j_end = j_end;
+    a.pat_bytes = pl->d_pat_bytes;
+    a.pat_off = pl->d_pat_off;
+    a.pat_len = pl->d_pat_len;
+    a.k = pl->k;
+    a.counts = pl->d_counts;
+
+    // ---- truncated tail windows of the bit-parallel patterns
+    if (!pl->tail_list.empty() && pl->tail_width > 0) {
+        const long long tail_first = std::max<long long>(0, n_total - pl->tail_mmax + 1);
+        if (j_end > tail_first && j_end > j_begin) {
+            const size_t per_thread = (size_t)(pl->tail_mmax + 1) * 4;
+            long long max_threads = std::max<long long>(pl->tail_width, (long long)(budget / per_thread));
+            int pats_per_launch = (int)std::max<long long>(1, max_threads / pl->tail_width);
+            for (size_t p0 = 0; p0 < pl->tail_list.size(); p0 += pats_per_launch) {
+                const int np = (int)std::min<size_t>(pats_per_launch, pl->tail_list.size() - p0);
+                const long long threads = (long long)np * pl->tail_width;
+                const unsigned blocks = (unsigned)((threads + 127) / 128);
+                const long long stride = (long long)blocks * 128;
+                int rc = ensure_scratch(pl, (size_t)stride * per_thread);
+                if (rc) return rc;
+                a.pat_list = pl->d_tail_list + p0;
+                a.npat = np;
+                a.tail_width = pl->tail_width;
+                a.scratch = pl->d_scratch;
+                a.scratch_stride = stride;
+                dp_tail_kernel<<<blocks, 128, 0, st>>>(a);
+                CUDA_TRY(cudaGetLastError());
+                g_launches++;
+            }
+        }
+    }
+    // ---- patterns evaluated entirely by the DP kernel (too long for the bit-parallel kernel, or
+    //      option kernel=dp)
+    if (!pl->all_list.empty() && j_end > j_begin) {
+        const size_t per_thread = (size_t)(pl->all_mmax + 1) * 4;
+        const long long nwin = j_end - j_begin;
+        long long max_threads = std::max<long long>(128, (long long)(budget / per_thread));
+        long long nx_blocks = std::min<long long>((nwin + 127) / 128, std::max<long long>(1, max_threads / 128));
+        nx_blocks = std::min<long long>(nx_blocks, (long long)pl->num_sms * 16);
+        const long long nx = nx_blocks * 128;
+        int pats_per_launch = (int)std::max<long long>(1, std::min<long long>(65535, max_threads / nx));
+        for (size_t p0 = 0; p0 < pl->all_list.size(); p0 += pats_per_launch) {
+            const int np = (int)std::min<size_t>(pats_per_launch, pl->all_list.size() - p0);
+            const long long stride = nx * np;
+            int rc = ensure_scratch(pl, (size_t)stride * per_thread);
+            if (rc) return rc;
+            a.pat_list = pl->d_all_list + p0;
+            a.npat = np;
+            a.tail_width = 0;
+            a.scratch = pl->d_scratch;
+            a.scratch_stride = stride;
+            dp_all_kernel<<<dim3((unsigned)nx_blocks, (unsigned)np), 128, 0, st>>>(a);
+            CUDA_TRY(cudaGetLastError());
+            g_launches++;
+        }
+    }
+    return APM_OK;
+}
+
+int check_patterns(const char *const *patterns, const int *pattern_len, int nb_patterns, int approx_factor) {
+    if (approx_factor < 0) return fail(APM_EINVAL, "approx_factor must be >= 0 (got %d)", approx_factor);
+    if (nb_patterns < 0) return fail(APM_EINVAL, "nb_patterns must be >= 0");
+    if (nb_patterns > 0 && (!patterns || !pattern_len)) return fail(APM_EINVAL, "patterns / pattern_len is NULL");
+    for (int i = 0; i < nb_patterns; ++i) {
+        if (!patterns[i] || pattern_len[i] <= 0)
+            return fail(APM_EINVAL, "pattern %d is empty (the reference rejects it too: sequential.c:65)", i);
+    }
+    return APM_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char *apm_last_error(void) { return tl_err.c_str(); }
+const char *apm_version(void) { return "apm_b200 0.1 (sm_100a)"; }
+unsigned long long apm_launch_count(void) { return g_launches.load(); }
+
+int apm_device_count(int *count) {
+    if (!count) return fail(APM_EINVAL, "count is NULL");
+    int n = 0;
+    int rc = device_ready(&n);
+    *count = rc ? 0 : n;
+    return rc;
+}
+
+int apm_set_option(const char *key, const char *value) {
+    if (!key || !value) return fail(APM_EINVAL, "key/value is NULL");
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    const std::string k = key, v = value;
+    auto bad = [&]() { return fail(APM_EINVAL, "bad value '%s' for option '%s'", value, key); };
+    if (k == "gpus") {
+        if (v == "all") g_opt.gpus = 0;
+        else {
+            int n = atoi(value);
+            if (n < 1 || n > 64) return bad();
+            g_opt.gpus = n;
+        }
+    } else if (k == "shard") {
+        if (v == "auto") g_opt.shard = SHARD_AUTO;
+        else if (v == "db" || v == "DB_OVER_RANKS") g_opt.shard = SHARD_DB;
+        else if (v == "patterns" || v == "PATTERNS_OVER_RANKS") g_opt.shard = SHARD_PATTERNS;
+        else return bad();
+    } else if (k == "kernel") {
+        if (v == "myers") g_opt.kernel = KERNEL_MYERS;
+        else if (v == "dp") g_opt.kernel = KERNEL_DP;
+        else return bad();
+    } else if (k == "mode") {
+        if (v == "direct") g_opt.mode = MODE_DIRECT;
+        else return bad();  // "filter" is not built yet
+    } else if (k == "rblock") {
+        if (v == "auto") g_opt.rblock = 0;
+        else if (v == "1" || v == "2" || v == "4") g_opt.rblock = atoi(value);
+        else return bad();
+    } else if (k == "tile") {
+        if (v == "auto") g_opt.tile = 0;
+        else {
+            int t = atoi(value);
+            if (t < kThreads || t % kThreads || t > 16384) return bad();
+            g_opt.tile = t;
+        }
+    } else if (k == "dp_scratch_mb") {
+        long long mb = atoll(value);
+        if (mb < 1 || mb > 65536) return bad();
+        g_opt.dp_scratch_mb = mb;
+    } else {
+        return fail(APM_EINVAL, "unknown option '%s'", key);
+    }
+    return APM_OK;
+}
+
+const char *apm_get_option(const char *key) {
+    if (!key) return nullptr;
+    const Options o = options_snapshot();
+    const std::string k = key;
+    if (k == "gpus") tl_optbuf = o.gpus ? std::to_string(o.gpus) : "all";
+    else if (k == "shard") tl_optbuf = o.shard == SHARD_DB ? "db" : (o.shard == SHARD_PATTERNS ? "patterns" : "auto");
+    else if (k == "kernel") tl_optbuf = o.kernel == KERNEL_DP ? "dp" : "myers";
+    else if (k == "mode") tl_optbuf = "direct";
+    else if (k == "rblock") tl_optbuf = o.rblock ? std::to_string(o.rblock) : "auto";
+    else if (k == "tile") tl_optbuf = o.tile ? std::to_string(o.tile) : "auto";
+    else if (k == "dp_scratch_mb") tl_optbuf = std::to_string(o.dp_scratch_mb);
+    else return nullptr;
+    return tl_optbuf.c_str();
+}
+
+// ---------------------------------------------------------------------------------------------------
+int apm_plan_create(const char *const *patterns, const int *pattern_len, int nb_patterns, int approx_factor,
+                    apm_plan **plan_out) {
+    if (!plan_out) return fail(APM_EINVAL, "plan_out is NULL");
+    *plan_out = nullptr;
+    int rc = check_patterns(patterns, pattern_len, nb_patterns, approx_factor);
+    if (rc) return rc;
+    int ndev = 0;
+    if ((rc = device_ready(&ndev))) return rc;
+
+    apm_plan *pl = new (std::nothrow) apm_plan();
+    if (!pl) return fail(APM_ENOMEM, "out of host memory");
+    pl->opt = options_snapshot();
+    pl->P = nb_patterns;
+    pl->k = approx_factor;
+    cudaError_t e = cudaGetDevice(&pl->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, pl->device);
+    if (e != cudaSuccess) {
+        delete pl;
+        return fail(APM_ECUDA, "cudaGetDevice/attribute: %s", cudaGetErrorString(e));
+    }
+    // per-call compact alphabet: codes 0..A-1 for the bytes that occur in some pattern, code A =
+    // "any other byte" (its Peq is all-zero); with all 256 bytes in use there is no "other".
+    bool used[256] = {false};
+    std::vector<uint8_t> flat;
+    std::vector<long long> off(nb_patterns);
+    std::vector<int> len(nb_patterns);
+    for (int i = 0; i < nb_patterns; ++i) {
+        pl->pats.emplace_back(patterns[i], (size_t)pattern_len[i]);
+        off[i] = (long long)flat.size();
+        len[i] = pattern_len[i];
+        for (int x = 0; x < pattern_len[i]; ++x) {
+            used[(uint8_t)patterns[i][x]] = true;
+            flat.push_back((uint8_t)patterns[i][x]);
+        }
+        pl->mmax_all_patterns = std::max(pl->mmax_all_patterns, pattern_len[i]);
+    }
+    int A = 0;
+    for (int b = 0; b < 256; ++b)
+        if (used[b]) pl->code_of[b] = (uint8_t)A++;
+    pl->ncodes = A < 256 ? A + 1 : 256;
+    for (int b = 0; b < 256; ++b)
+        if (!used[b]) pl->code_of[b] = (uint8_t)A;  // only reachable when A < 256
+
+    auto cleanup_fail = [&](int code) {
+        apm_plan_destroy(pl);
+        return code;
+    };
+    std::vector<uint8_t> map(pl->code_of, pl->code_of + 256);
+    if ((rc = upload(&pl->d_code_of, map))) return cleanup_fail(rc);
+    if ((rc = upload(&pl->d_pat_bytes, flat))) return cleanup_fail(rc);
+    if ((rc = upload(&pl->d_pat_off, off))) return cleanup_fail(rc);
+    if ((rc = upload(&pl->d_pat_len, len))) return cleanup_fail(rc);
+    e = cudaMalloc((void **)&pl->d_counts, sizeof(unsigned long long) * std::max(1, nb_patterns));
+    if (e == cudaSuccess) e = cudaMemset(pl->d_counts, 0, sizeof(unsigned long long) * std::max(1, nb_patterns));
+    if (e != cudaSuccess) {
+        fail(APM_ECUDA, "allocating counters: %s", cudaGetErrorString(e));
+        return cleanup_fail(APM_ECUDA);
+    }
+    if ((rc = build_work(pl))) return cleanup_fail(rc);
+    *plan_out = pl;
+    return APM_OK;
+}
+
+int apm_plan_destroy(apm_plan *pl) {
+    if (!pl) return APM_OK;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(pl->device);
+    free_work(pl);
+    cudaFree(pl->d_code_of);
+    cudaFree(pl->d_pat_bytes);
+    cudaFree(pl->d_pat_off);
+    cudaFree(pl->d_pat_len);
+    cudaFree(pl->d_counts);
+    cudaFree(pl->d_scratch);
+    cudaSetDevice(cur);
+    delete pl;
+    return APM_OK;
+}
+
+int apm_plan_set_pattern_shard(apm_plan *pl, int rank, int world) {
+    if (!pl) return fail(APM_EINVAL, "plan is NULL");
+    if (world < 1 || rank < 0 || rank >= world) return fail(APM_EINVAL, "bad pattern shard %d/%d", rank, world);
+    CUDA_TRY(cudaSetDevice(pl->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    pl->shard_rank = rank;
+    pl->shard_world = world;
+    return build_work(pl);
+}
+
+int apm_plan_zero_counts(apm_plan *pl, void *stream) {
+    if (!pl) return fail(APM_EINVAL, "plan is NULL");
+    CUDA_TRY(cudaMemsetAsync(pl->d_counts, 0, sizeof(unsigned long long) * std::max(1, pl->P), (cudaStream_t)stream));
+    return APM_OK;
+}
+
+int apm_plan_counts_device_ptr(apm_plan *pl, unsigned long long **d_counts) {
+    if (!pl || !d_counts) return fail(APM_EINVAL, "NULL argument");
+    *d_counts = pl->d_counts;
+    return APM_OK;
+}
+
+int apm_plan_read_counts(apm_plan *pl, long long *n_matches, void *stream) {
+    if (!pl || (!n_matches && pl->P > 0)) return fail(APM_EINVAL, "NULL argument");
+    if (pl->P == 0) return APM_OK;
+    CUDA_TRY(cudaMemcpyAsync(n_matches, pl->d_counts, sizeof(long long) * pl->P, cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return APM_OK;
+}
+
+int apm_plan_max_pattern_len(apm_plan *pl, int *m_max) {
+    if (!pl || !m_max) return fail(APM_EINVAL, "NULL argument");
+    *m_max = pl->mmax_all_patterns;
+    return APM_OK;
+}
+
+int apm_plan_count_device(apm_plan *pl, const unsigned char *d_buf, unsigned long long buf_offset,
+                          unsigned long long buf_len, unsigned long long n_total, unsigned long long j_begin,
+                          unsigned long long j_end, void *stream) {
+    if (!pl) return fail(APM_EINVAL, "plan is NULL");
+    if (n_total > (1ull << 62) || buf_offset > n_total || buf_len > n_total - buf_offset)
+        return fail(APM_EINVAL, "buffer [%llu, +%llu) is not inside the text of %llu bytes", buf_offset, buf_len, n_total);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long N = (long long)n_total;
+    long long je = (long long)std::min<unsigned long long>(j_end, n_total);
+    je = std::min(je, N - (long long)pl->k);  // sequential.c:121
+    const long long jb = (long long)j_begin;
+    if (pl->P == 0 || je <= jb) return APM_OK;
+    // bytes the windows [jb, je) may touch
+    const long long need_end = std::min(N, je + (long long)pl->mmax_all_patterns - 1);
+    if ((long long)buf_offset > jb || (long long)(buf_offset + buf_len) < need_end)
+        return fail(APM_EINVAL,
+                    "device buffer [%llu, %llu) does not cover window starts [%lld, %lld) plus the %d-byte halo",
+                    buf_offset, buf_offset + buf_len, jb, je, pl->mmax_all_patterns - 1);
+    if (!d_buf) return fail(APM_EINVAL, "d_buf is NULL");
+    int cur = -1;
+    CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != pl->device) CUDA_TRY(cudaSetDevice(pl->device));
+    int rc = APM_OK;
+    for (auto &b : pl->buckets) {
+        rc = launch_myers(pl, b, d_buf, (long long)buf_len, N - (long long)buf_offset, jb - (long long)buf_offset,
+                          je - (long long)buf_offset, st);
+        if (rc) break;
+    }
+    if (!rc) rc = launch_dp(pl, d_buf, (long long)buf_offset, N, jb, je, st);
+    if (cur != pl->device) cudaSetDevice(cur);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int apm_synth_text_device(unsigned char *d_out, unsigned long long seed, unsigned long long offset,
+                          unsigned long long count, void *stream) {
+    int ndev = 0;
+    int rc = device_ready(&ndev);
+    if (rc) return rc;
+    if (count == 0) return APM_OK;
+    if (!d_out) return fail(APM_EINVAL, "d_out is NULL");
+    const unsigned long long nvec = (count + 15) / 16;
+    const unsigned blocks = (unsigned)std::min<unsigned long long>((nvec + 255) / 256, 148ull * 32);
+    synth_text_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_out, seed, offset, count);
+    CUDA_TRY(cudaGetLastError());
+    g_launches++;
+    return APM_OK;
+}
+
+int apm_int_peak(int kind, double *ops_per_sec, double *seconds) {
+    int ndev = 0;
+    int rc = device_ready(&ndev);
+    if (rc) return rc;
+    if (kind < 0 || kind > 3 || !ops_per_sec) return fail(APM_EINVAL, "bad argument");
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    uint32_t *d_out = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d_out, 64));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = sms * 8;
+    const double ops_per_thread_iter = (kind == 0 || kind == 3) ? 2.0 * 8 * 8 : 1.0 * 8 * 8;
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {  // rep 0 = warm-up
+        CUDA_TRY(cudaEventRecord(e0));
+        switch (kind) {
+            case 0: int_peak_kernel<0><<<blocks, 256>>>(d_out, iters, 0x9E3779B9u + rep, 0x7F4A7C15u); break;
+            case 1: int_peak_kernel<1><<<blocks, 256>>>(d_out, iters, 0x9E3779B9u + rep, 0x7F4A7C15u); break;
+            case 2: int_peak_kernel<2><<<blocks, 256>>>(d_out, iters, 0x9E3779B9u + rep, 0x7F4A7C15u); break;
+            default: int_peak_kernel<3><<<blocks, 256>>>(d_out, iters, 0x9E3779B9u + rep, 0x7F4A7C15u); break;
+        }
+        CUDA_TRY(cudaGetLastError());
+        g_launches++;
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best_ms = std::min(best_ms, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    const double total_ops = ops_per_thread_iter * iters * 256.0 * blocks;
+    *ops_per_sec = total_ops / (best_ms * 1e-3);
+    if (seconds) *seconds = best_ms * 1e-3;
+    return APM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One-shot host API
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct DevJob {
+    int dev = 0;
+    cudaStream_t st = nullptr;
+    apm_plan *plan = nullptr;
+    uint8_t *d_text = nullptr;
+    long long j0 = 0, j1 = 0, b0 = 0, b1 = 0;  // window-start range and byte range (global)
+};
+
+void release_jobs(std::vector<DevJob> &jobs, int restore_dev) {
+    for (auto &j : jobs) {
+        cudaSetDevice(j.dev);
+        if (j.plan) apm_plan_destroy(j.plan);
+        if (j.d_text) cudaFree(j.d_text);
+        if (j.st) cudaStreamDestroy(j.st);
+    }
+    jobs.clear();
+    cudaSetDevice(restore_dev);
+}
+
+// Text source: either a host buffer or a file descriptor.
+struct TextSource {
+    const unsigned char *host = nullptr;
+    int fd = -1;
+};
+
+int copy_range_to_device(const TextSource &src, long long b0, long long b1, uint8_t *d_dst, cudaStream_t st) {
+    if (b1 <= b0) return APM_OK;
+    if (src.host) {
+        CUDA_TRY(cudaMemcpyAsync(d_dst, src.host + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
+        return APM_OK;
+    }
+    // file: pread into two pinned staging buffers, async H2D, so disk/page-cache reads overlap the copy
+    const size_t chunk = (size_t)32 << 20;
+    uint8_t *pin[2] = {nullptr, nullptr};
+    cudaEvent_t done[2];
+    CUDA_TRY(cudaMallocHost((void **)&pin[0], chunk));
+    CUDA_TRY(cudaMallocHost((void **)&pin[1], chunk));
+    CUDA_TRY(cudaEventCreate(&done[0]));
+    CUDA_TRY(cudaEventCreate(&done[1]));
+    int rc = APM_OK, s = 0;
+    bool used[2] = {false, false};
+    for (long long pos = b0; pos < b1 && !rc; s ^= 1) {
+        const size_t want = (size_t)std::min<long long>((long long)chunk, b1 - pos);
+        if (used[s]) cudaEventSynchronize(done[s]);
+        size_t got = 0;
+        while (got < want) {
+            ssize_t r = pread(src.fd, pin[s] + got, want - got, (off_t)(pos + (long long)got));
+            if (r <= 0) {
+                rc = fail(APM_EIO, "short read at byte %lld", pos + (long long)got);
+                break;
+            }
+            got += (size_t)r;
+        }
+        if (rc) break;
+        cudaError_t e = cudaMemcpyAsync(d_dst + (pos - b0), pin[s], want, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(done[s], st);
+        if (e != cudaSuccess) rc = fail(APM_ECUDA, "H2D copy: %s", cudaGetErrorString(e));
+        used[s] = true;
+        pos += (long long)want;
+    }
+    cudaStreamSynchronize(st);
+    cudaEventDestroy(done[0]);
+    cudaEventDestroy(done[1]);
+    cudaFreeHost(pin[0]);
+    cudaFreeHost(pin[1]);
+    return rc;
+}
+
+int count_impl(const TextSource &src, long long N, const char *const *patterns, const int *pattern_len,
+               int nb_patterns, int approx_factor, long long *n_matches) {
+    int rc = check_patterns(patterns, pattern_len, nb_patterns, approx_factor);
+    if (rc) return rc;
+    if (nb_patterns > 0 && !n_matches) return fail(APM_EINVAL, "n_matches is NULL");
+    int ndev = 0;
+    if ((rc = device_ready(&ndev))) return rc;
+    for (int i = 0; i < nb_patterns; ++i) n_matches[i] = 0;
+    const long long W = N - approx_factor;  // window starts (sequential.c:121)
+    if (nb_patterns == 0 || W <= 0) return APM_OK;
+
+    const Options opt = options_snapshot();
+    int G = opt.gpus == 0 ? ndev : std::min(opt.gpus, ndev);
+    int mmax = 0;
+    for (int i = 0; i < nb_patterns; ++i) mmax = std::max(mmax, pattern_len[i]);
+    int shard = opt.shard;
+    if (shard == SHARD_AUTO)  // text shards when every GPU still gets a few tiles per SM (replaces main.c:88-123)
+        shard = (W / G >= (long long)148 * 4 * 1024 || nb_patterns < G) ? SHARD_DB : SHARD_PATTERNS;
+    if (shard == SHARD_PATTERNS) G = std::min(G, nb_patterns);
+    if (shard == SHARD_DB) G = (int)std::min<long long>(G, W);
+
+    int restore = 0;
+    cudaGetDevice(&restore);
+    std::vector<DevJob> jobs(G);
+    auto bail = [&](int code) {
+        std::string keep = tl_err;
+        release_jobs(jobs, restore);
+        tl_err = keep;
+        return code;
+    };
+    for (int g = 0; g < G; ++g) {
+        DevJob &j = jobs[g];
+        j.dev = g;
+        if (cudaSetDevice(g) != cudaSuccess) return bail(fail(APM_ECUDA, "cudaSetDevice(%d) failed", g));
+        if (cudaStreamCreateWithFlags(&j.st, cudaStreamNonBlocking) != cudaSuccess)
+            return bail(fail(APM_ECUDA, "cudaStreamCreate failed on device %d", g));
+        if ((rc = apm_plan_create(patterns, pattern_len, nb_patterns, approx_factor, &j.plan))) return bail(rc);
+        if (shard == SHARD_PATTERNS) {
+            if (G > 1 && (rc = apm_plan_set_pattern_shard(j.plan, g, G))) return bail(rc);
+            j.j0 = 0;
+            j.j1 = W;
+        } else {  // database shard g owns window STARTS [j0, j1); bytes up to j1 + mmax - 1 (halo)
+            j.j0 = (W * g / G) & ~15ll;
+            j.j1 = g == G - 1 ? W : ((W * (g + 1) / G) & ~15ll);
+        }
+        j.b0 = j.j0;
+        j.b1 = std::min(N, j.j1 + mmax - 1);
+        if (cudaMalloc((void **)&j.d_text, (size_t)std::max<long long>(16, j.b1 - j.b0)) != cudaSuccess)
+            return bail(fail(APM_ENOMEM, "cudaMalloc of %lld text bytes failed on device %d", j.b1 - j.b0, g));
+        if ((rc = copy_range_to_device(src, j.b0, j.b1, j.d_text, j.st))) return bail(rc);
+        if ((rc = apm_plan_count_device(j.plan, j.d_text, (unsigned long long)j.b0, (unsigned long long)(j.b1 - j.b0),
+                                        (unsigned long long)N, (unsigned long long)j.j0, (unsigned long long)j.j1, j.st)))
+            return bail(rc);
+    }
+    std::vector<long long> part(nb_patterns);
+    for (int g = 0; g < G; ++g) {
+        cudaSetDevice(jobs[g].dev);
+        if ((rc = apm_plan_read_counts(jobs[g].plan, part.data(), jobs[g].st))) return bail(rc);
+        for (int i = 0; i < nb_patterns; ++i) n_matches[i] += part[i];
+    }
+    release_jobs(jobs, restore);
+    return APM_OK;
+}
+
+}  // namespace
+
+int apm_count_matches(const unsigned char *text, size_t n_bytes, const char *const *patterns,
+                      const int *pattern_len, int nb_patterns, int approx_factor, long long *n_matches) {
+    if (!text && n_bytes > 0) return fail(APM_EINVAL, "text is NULL");
+    TextSource src;
+    static const unsigned char empty = 0;
+    src.host = text ? text : &empty;
+    return count_impl(src, (long long)n_bytes, patterns, pattern_len, nb_patterns, approx_factor, n_matches);
+}
+
+int apm_count_matches_file(const char *path, const char *const *patterns, const int *pattern_len,
+                           int nb_patterns, int approx_factor, long long *n_matches,
+                           unsigned long long *n_bytes_out) {
+    if (!path) return fail(APM_EINVAL, "path is NULL");
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(APM_EIO, "Unable to open the text file <%s>", path);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) {
+        close(fd);
+        return fail(APM_EIO, "Unable to stat the text file <%s>", path);
+    }
+    if (n_bytes_out) *n_bytes_out = (unsigned long long)sb.st_size;
+    TextSource src;
+    src.fd = fd;
+    const int rc = count_impl(src, (long long)sb.st_size, patterns, pattern_len, nb_patterns, approx_factor, n_matches);
+    close(fd);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// apm_dp.cuh -- explicit-DP fallback kernels (BASELINE north_star item 2).
+//
+// Evaluates src/utils.c:76-99 cell by cell for (a) the truncated tail windows of every pattern
+// (src/sequential.c:131-134: size = n_bytes - j < m, the pattern PREFIX of that size is compared),
+// (b) every window of patterns longer than the bit-parallel kernel supports (m > 32*kMaxWords), and
+// (c) everything when option kernel=dp is set (an in-GPU cross-check of the bit-parallel kernel).
+//
+// One thread per (pattern, window).  The DP column of a thread lives in a global scratch array laid
+// out [row][thread] so that the row sweep of a warp is coalesced and stays in L1/L2; unlike the
+// reference's GPU clone (patterns_over_ranks.cu:31) there is no device-heap malloc, and the count is
+// a proper 64-bit atomic (the reference's `(*local_matches)++` at :68 is a data race).
+#pragma once
+#include "apm_common.cuh"
+
+namespace apm {
+
+#ifdef __CUDACC__
+
+struct DpArgs {
+    const uint8_t *buf;           // device text; buf[0] = global byte buf_offset
+    long long buf_offset;         // global index of buf[0]
+    long long n_total;            // global text length
+    long long j_begin, j_end;     // global window-start range, already clamped to n_total - k
+    const uint8_t *pat_bytes;     // all patterns, concatenated
+    const long long *pat_off;     // [P]
+    const int *pat_len;           // [P]
+    const int *pat_list;          // patterns handled by this launch
+    int npat;
+    int k;
+    int tail_width;               // tail mode: window slots per pattern (>= max m-1-k)
+    uint32_t *scratch;            // [(mmax+1)][scratch_stride]
+    long long scratch_stride;     // = total threads of the launch
+    unsigned long long *counts;
+};
+
+// Distance of pattern[0..size) vs text window [j, j+size): the DP of utils.c:76-99 with the column
+// in scratch[row * stride].  Rows/cols are 1-based as in the reference.
+__device__ __forceinline__ uint32_t dp_window(const uint8_t *__restrict__ pat, const uint8_t *__restrict__ win,
+                                              int size, uint32_t *__restrict__ col, long long stride) {
+    for (int r = 1; r <= size; ++r) col[(long long)r * stride] = (uint32_t)r;
+    uint32_t last = (uint32_t)size;
+    for (int c = 1; c <= size; ++c) {
+        const uint32_t tc = win[c - 1];
+        uint32_t diag = (uint32_t)(c - 1);  // D[0][c-1]
+        uint32_t up = (uint32_t)c;          // D[0][c]
+        for (int r = 1; r <= size; ++r) {
+            const uint32_t left = col[(long long)r * stride];  // D[r][c-1]
+            const uint32_t sub = diag + (pat[r - 1] == tc ? 0u : 1u);
+            const uint32_t v = min(sub, min(left, up) + 1u);
+            col[(long long)r * stride] = v;
+            diag = left;
+            up = v;
+        }
+        last = up;
+    }
+    return last;
+}
+
+// Tail mode: thread (p, t) evaluates window j = max(0, n_total - m_p + 1) + t if it lies in
+// [j_begin, j_end).  All such windows are truncated (size < m) -- or the whole text is shorter
+// than the pattern.
+__global__ void __launch_bounds__(128) dp_tail_kernel(const DpArgs a) {
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)a.npat * a.tail_width;
+    if (gtid >= total) return;
+    const int pi = (int)(gtid / a.tail_width);
+    const int t = (int)(gtid % a.tail_width);
+    const int p = a.pat_list[pi];
+    const int m = a.pat_len[p];
+    const long long first = a.n_total - m + 1 > 0 ? a.n_total - m + 1 : 0;
+    const long long j = first + t;
+    if (j < a.j_begin || j >= a.j_end) return;
+    const long long left = a.n_total - j;
+    const int size = left < m ? (int)left : m;
+    const uint32_t d = dp_window(a.pat_bytes + a.pat_off[p], a.buf + (j - a.buf_offset), size,
+                                 a.scratch + gtid, a.scratch_stride);
+    if (d <= (uint32_t)a.k) atomicAdd(&a.counts[p], 1ull);
+}
+
+// All-windows mode: blockIdx.y = pattern slot, grid-stride over window starts [j_begin, j_end).
+__global__ void __launch_bounds__(128) dp_all_kernel(const DpArgs a) {
+    const int p = a.pat_list[blockIdx.y];
+    const int m = a.pat_len[p];
+    const uint8_t *pat = a.pat_bytes + a.pat_off[p];
+    const long long tx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nx = (long long)gridDim.x * blockDim.x;
+    uint32_t *col = a.scratch + ((long long)blockIdx.y * nx + tx);
+    unsigned int hits = 0;
+    for (long long j = a.j_begin + tx; j < a.j_end; j += nx) {
+        const long long left = a.n_total - j;
+        const int size = left < m ? (int)left : m;
+        const uint32_t d = dp_window(pat, a.buf + (j - a.buf_offset), size, col, a.scratch_stride);
+        hits += (d <= (uint32_t)a.k);
+    }
+    // warp-aggregate (all lanes of a warp share the pattern)
+    for (int o = 16; o > 0; o >>= 1) hits += __shfl_down_sync(0xFFFFFFFFu, hits, o);
+    if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&a.counts[p], (unsigned long long)hits);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace apm

@@ -1,0 +1,80 @@
+// apm_util_kernels.cuh -- synthetic-text generator and the integer-ALU peak microbenchmark.
+#pragma once
+#include "apm_common.cuh"
+
+namespace apm {
+
+#ifdef __CUDACC__
+
+// text[i] = "ACGT"[splitmix64(seed + i) >> 62]  (SURVEY.md section 8d).  16 bytes per thread per
+// iteration, stored as one uint4 when aligned; HBM-write bound.
+__global__ void __launch_bounds__(256) synth_text_kernel(uint8_t *out, unsigned long long seed,
+                                                         unsigned long long offset, unsigned long long count) {
+    const unsigned long long nvec = (count + 15) / 16;
+    const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+         v += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long i0 = v * 16;
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t s = (uint32_t)(splitmix64(seed + offset + i0 + 4 * q + b) >> 62);
+                // 'A'=0x41 'C'=0x43 'G'=0x47 'T'=0x54 packed in one constant, selected by 8*s
+                x |= ((0x54474341u >> (8 * s)) & 0xFFu) << (8 * b);
+            }
+            w[q] = x;
+        }
+        if (aligned && i0 + 16 <= count) {
+            reinterpret_cast<uint4 *>(out)[v] = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (int b = 0; b < 16 && i0 + b < count; ++b) out[i0 + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Integer-ALU peak: ILP independent chains per thread, no memory traffic inside the loop.
+//   kind 0: lop3 + add alternating        (the roofline denominator: "LOP3+IADD3")
+//   kind 1: lop3 only
+//   kind 2: add only   (ptxas may place some adds on the FMA pipe as IMAD.IADD)
+//   kind 3: lop3 + mad.lo alternating     (ALU pipe + FMA pipe together)
+// Every iteration executes 2*ILP integer instructions per thread for kinds 0 and 3, ILP otherwise.
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters, uint32_t b, uint32_t c) {
+    constexpr int ILP = 8;
+    uint32_t a[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) a[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) {
+                if constexpr (KIND == 0) {
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+                    asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(c));
+                } else if constexpr (KIND == 1) {
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+                } else if constexpr (KIND == 2) {
+                    asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(c));
+                } else {
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                }
+            }
+        }
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) x ^= a[i];
+    if (x == 0x12345678u) out[0] = x;  // practically never true; keeps the chains alive
+}
+
+#endif  // __CUDACC__
+
+}  // namespace apm

@@ -1,0 +1,297 @@
+"""GPU parity tests: the CUDA path (through the C-ABI of libapm_b200.so) against the CPU oracle and the
+committed golden vectors produced by the reference's own apm_sequential.  Bit-exact (integer counts)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import apm_b200
+from oracle import oracle
+from tests.golden_util import cases, fixtures
+
+pytestmark = pytest.mark.gpu
+
+FX = fixtures()
+CASES = cases()
+
+
+@pytest.fixture(autouse=True)
+def _default_options():
+    for k, v in (("kernel", "myers"), ("rblock", "auto"), ("tile", "auto"), ("gpus", "1"), ("shard", "auto")):
+        apm_b200.set_option(k, v)
+    yield
+
+
+def _torch():
+    import torch
+    return torch
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors (reference apm_sequential outputs)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c["name"])
+def test_golden_host_api(case):
+    before = apm_b200.launch_count()
+    got = apm_b200.count_matches(FX[case["text"]], case["patterns"], case["k"])
+    assert got == case["expected"]
+    assert apm_b200.launch_count() > before, "no CUDA kernel launched"
+
+
+@pytest.mark.parametrize("name", ["config1_readme", "easy_k2", "small_k25", "small_m200_k10", "config2"])
+def test_golden_dp_kernel(name):
+    """The explicit-DP fallback kernel alone reproduces the reference too (north_star item 2)."""
+    case = next(c for c in CASES if c["name"] == name)
+    apm_b200.set_option("kernel", "dp")
+    assert apm_b200.count_matches(FX[case["text"]], case["patterns"], case["k"]) == case["expected"]
+
+
+@pytest.mark.parametrize("rblock", ["1", "2", "4"])
+@pytest.mark.parametrize("name", ["config1_readme", "x100_m64_k4", "small_m200_k10", "small_k2"])
+def test_golden_every_register_blocking(name, rblock):
+    case = next(c for c in CASES if c["name"] == name)
+    apm_b200.set_option("rblock", rblock)
+    assert apm_b200.count_matches(FX[case["text"]], case["patterns"], case["k"]) == case["expected"]
+
+
+def test_cli_drop_in(tmp_path):
+    """`apm` prints what sequential.c:79-82,151,157-160 prints (timing value aside)."""
+    case = next(c for c in CASES if c["name"] == "config1_readme")
+    f = tmp_path / "small_chrY_x100.fa"
+    f.write_bytes(FX[case["text"]])
+    argv = [apm_b200.CLI_PATH, str(case["k"]), str(f)] + [p.decode() for p in case["patterns"]]
+    r = subprocess.run(argv, capture_output=True, text=True, check=True)
+    lines = r.stdout.splitlines()
+    assert lines[0] == (f"Approximate Pattern Mathing: looking for {len(case['patterns'])} pattern(s) "
+                        f"in file {f} w/ distance of {case['k']}")
+    assert re.fullmatch(r"APM done in \d+\.\d{6} s", lines[1])
+    want = [f"Number of matches for pattern <{p.decode()}>: {n}" for p, n in zip(case["patterns"], case["expected"])]
+    assert lines[2:] == want
+    # trailing approach flag of the parallel binary (main.c:66-85) is accepted and not searched for
+    r2 = subprocess.run(argv + ["DB_OVER_RANKS"], capture_output=True, text=True, check=True)
+    assert r2.stdout.splitlines()[2:] == want
+    r3 = subprocess.run(argv + ["PATTERNS_OVER_RANKS"], capture_output=True, text=True, check=True)
+    assert r3.stdout.splitlines()[2:] == want
+
+
+def test_file_api(tmp_path):
+    case = next(c for c in CASES if c["name"] == "x100_k2")
+    f = tmp_path / "t.fa"
+    f.write_bytes(FX[case["text"]])
+    assert apm_b200.count_matches_file(str(f), case["patterns"], case["k"]) == case["expected"]
+    with pytest.raises(apm_b200.ApmError) as ei:
+        apm_b200.count_matches_file(str(tmp_path / "missing.fa"), [b"A"], 0)
+    assert ei.value.code == apm_b200.APM_EIO
+
+
+# ---------------------------------------------------------------------------------------------
+# edge semantics S4-S8 of SURVEY.md
+# ---------------------------------------------------------------------------------------------
+EDGE = [
+    (b"ACGTACGTAC", [b"AC"], 2),             # m <= k: every start matches (n - k)
+    (b"ACGTACGTAC", [b"AC"], 10),            # k >= n: no window
+    (b"ACGTACGTAC", [b"AC"], 11),
+    (b"GGGGGGAC", [b"ACGT"], 0),             # suffix == pattern prefix counts (tail truncation)
+    (b"ACG", [b"ACGTTTTT"], 0),              # m > n
+    (b"ACG", [b"ACGTTTTT", b"A" * 300], 1),  # long pattern on a tiny text
+    (b"", [b"ACGT"], 0),                     # empty text
+    (b"A", [b"A", b"C", b"AA"], 0),
+    (bytes(range(256)) * 3, [bytes(range(100, 140)), bytes([255, 0, 1]), b"\n\n"], 1),  # all byte values
+    (b"AC\nGT\nAC\nGT\n" * 20, [b"C\nG", b"\nAC\nGT\nAC\nGT\nAC\nGT\nAC\nGT\nAC\nG", b"GT\n"], 1),
+]
+
+
+@pytest.mark.parametrize("idx", range(len(EDGE)))
+@pytest.mark.parametrize("kernel", ["myers", "dp"])
+def test_edge_cases(idx, kernel):
+    text, pats, k = EDGE[idx]
+    apm_b200.set_option("kernel", kernel)
+    assert apm_b200.count_matches(text, pats, k) == oracle.count_matches(text, pats, k)
+
+
+def test_alphabet_with_all_256_byte_values():
+    rng = np.random.default_rng(3)
+    text = rng.integers(0, 256, 5000, dtype=np.uint8).tobytes()
+    pats = [bytes(range(256)), text[100:140], text[4000:4033], bytes(rng.integers(0, 256, 70, dtype=np.uint8))]
+    for k in (0, 3):
+        assert apm_b200.count_matches(text, pats, k) == oracle.count_matches(text, pats, k)
+
+
+# ---------------------------------------------------------------------------------------------
+# randomized property test: GPU == oracle
+# ---------------------------------------------------------------------------------------------
+def _random_case(rng, max_n=3000):
+    alph = [b"ACGT", b"ACGT\n", b"AC", b"ACGTNacgt\n", bytes(range(256))][int(rng.integers(0, 5))]
+    al = np.frombuffer(alph, dtype=np.uint8)
+    n = int(rng.integers(0, max_n))
+    text = al[rng.integers(0, len(al), n)].tobytes()
+    pats = []
+    for _ in range(int(rng.integers(1, 9))):
+        m = int(rng.choice([1, 2, 5, 16, 31, 32, 33, 50, 63, 64, 65, 96, 100, 128, 129, 200, 256, 257, 300]))
+        if n > m and rng.random() < 0.7:
+            off = int(rng.integers(0, n - m))
+            p = bytearray(text[off:off + m])
+            for _ in range(int(rng.integers(0, 6))):
+                p[int(rng.integers(0, m))] = int(al[int(rng.integers(0, len(al)))])
+        else:
+            p = bytearray(al[rng.integers(0, len(al), m)].tobytes())
+        pats.append(bytes(p))
+    if n > 10 and rng.random() < 0.5:  # a pattern whose prefix is the text's suffix
+        cut = int(rng.integers(1, min(n, 60)))
+        pats.append(text[-cut:] + al[rng.integers(0, len(al), int(rng.integers(1, 40)))].tobytes())
+    k = int(rng.choice([0, 0, 1, 2, 4, 10, 40]))
+    return text, pats, k
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_vs_oracle(seed):
+    rng = np.random.default_rng(1000 + seed)
+    text, pats, k = _random_case(rng)
+    assert apm_b200.count_matches(text, pats, k) == oracle.count_matches(text, pats, k)
+
+
+def test_myers_vs_dp_kernel_large_slice():
+    """Kernel-vs-kernel on a slice far larger than the oracle can do in seconds."""
+    text = oracle.synth_text(0x5EED0001, 12345, 400_000).tobytes()
+    pats = [text[1000:1064], text[5000:5200], text[70000:70032], b"ACGT" * 16, text[-50:] + b"TTTT"]
+    k = 6
+    apm_b200.set_option("kernel", "dp")
+    dp = apm_b200.count_matches(text, pats, k)
+    apm_b200.set_option("kernel", "myers")
+    assert apm_b200.count_matches(text, pats, k) == dp
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident API: shards with halo, unaligned buffers, tiles
+# ---------------------------------------------------------------------------------------------
+def test_synth_text_device_matches_oracle_generator():
+    torch = _torch()
+    for off, cnt in ((0, 1000), (7, 4099), (123456789012, 65536 + 5)):
+        buf = torch.empty(cnt + 32, dtype=torch.uint8, device="cuda")
+        apm_b200.synth_text_device(buf.data_ptr() + 3, 0x5EED0001, off, cnt)  # unaligned destination
+        torch.cuda.synchronize()
+        got = buf[3:3 + cnt].cpu().numpy().tobytes()
+        assert got == oracle.synth_text(0x5EED0001, off, cnt).tobytes()
+
+
+@pytest.mark.parametrize("nshards,misalign", [(1, 0), (2, 1), (3, 5), (7, 15), (8, 0)])
+def test_db_shards_with_halo_are_exact(nshards, misalign):
+    """Sum over shards == unsharded; each shard sees only its own bytes + (m_max-1)-byte halo, at an
+    arbitrary (unaligned) device address; seams fall on / next to planted matches."""
+    torch = _torch()
+    n = 150_000
+    text = bytearray(oracle.synth_text(0x5EED0001, 999, n).tobytes())
+    pat64 = bytes(text[20000:20064])
+    pat200 = bytes(text[90000:90200])
+    W0 = n - 3
+    for g in range(1, nshards):  # plant an exact copy straddling every seam
+        seam = W0 * g // nshards
+        text[seam - 20:seam - 20 + 64] = pat64
+    text = bytes(text)
+    pats = [pat64, pat200, text[50:82], text[-30:] + b"ACGTAC"]
+    k = 3
+    want = oracle.count_matches(text, pats, k)
+    W = n - k
+    with apm_b200.Plan(pats, k) as plan:
+        for g in range(nshards):
+            j0, j1 = W * g // nshards, W * (g + 1) // nshards
+            b0, b1 = j0, min(n, j1 + plan.m_max - 1)
+            host = torch.frombuffer(bytearray(text[b0:b1]), dtype=torch.uint8)
+            dev = torch.empty(b1 - b0 + 64, dtype=torch.uint8, device="cuda")
+            dev[misalign:misalign + (b1 - b0)].copy_(host)
+            plan.count_device(dev.data_ptr() + misalign, b0, b1 - b0, n, j0, j1)
+        assert plan.read_counts() == want
+        # too small a buffer (halo missing) is rejected, not silently truncated
+        if nshards > 1:
+            j0, j1 = 0, W // nshards
+            dev = torch.zeros(j1, dtype=torch.uint8, device="cuda")
+            with pytest.raises(apm_b200.ApmError):
+                plan.count_device(dev.data_ptr(), 0, j1, n, j0, j1)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_pattern_shards_sum_to_whole(world):
+    torch = _torch()
+    text = oracle.synth_text(0x5EED0001, 5, 60_000).tobytes()
+    pats = [text[i * 997:i * 997 + m] for i, m in enumerate([32, 64, 64, 50, 200, 20, 64, 33, 100, 64, 300])]
+    k = 2
+    want = oracle.count_matches(text, pats, k)
+    dev = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    total = [0] * len(pats)
+    for r in range(world):
+        with apm_b200.Plan(pats, k) as plan:
+            plan.set_pattern_shard(r, world)
+            plan.count_device(dev.data_ptr(), 0, len(text), len(text), 0, len(text))
+            part = plan.read_counts()
+        assert all(part[i] == 0 for i in range(len(pats)) if i % world != r)
+        total = [a + b for a, b in zip(total, part)]
+    assert total == want
+
+
+@pytest.mark.parametrize("tile", ["256", "512", "2048", "4096"])
+def test_tile_sizes(tile):
+    case = next(c for c in CASES if c["name"] == "x100_k5")
+    apm_b200.set_option("tile", tile)
+    assert apm_b200.count_matches(FX[case["text"]], case["patterns"], case["k"]) == case["expected"]
+
+
+def test_counts_accumulate_and_zero():
+    torch = _torch()
+    text = FX["small_chrY"]
+    dev = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    pats = [b"ACGT", b"TTTT"]
+    one = oracle.count_matches(text, pats, 1)
+    with apm_b200.Plan(pats, 1) as plan:
+        for _ in range(3):
+            plan.count_device(dev.data_ptr(), 0, len(text), len(text), 0, len(text))
+        assert plan.read_counts() == [3 * x for x in one]
+        plan.zero_counts()
+        plan.count_device(dev.data_ptr(), 0, len(text), len(text), 0, len(text))
+        assert plan.read_counts() == one
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE-sized inputs: size-independent properties + sampled-slice oracle
+# ---------------------------------------------------------------------------------------------
+def test_large_synthetic_sampled_slices():
+    """64 MiB of the config-3 text, 32 patterns of length 64, k = 4: per-slice counts equal the oracle's
+    on random slices + the tail slice; planted patterns are found; sharding does not change anything."""
+    torch = _torch()
+    from tests.synth import make_patterns
+    n = 64 << 20
+    seed = 0x5EED0001
+    dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+    apm_b200.synth_text_device(dev.data_ptr(), seed, 0, n)
+    pats, offs, nsub = make_patterns(seed, n, 32, 64, 7)
+    k = 4
+    W = n - k
+    with apm_b200.Plan(pats, k) as plan:
+        plan.count_device(dev.data_ptr(), 0, n, n, 0, W)
+        whole = plan.read_counts()
+        for p in range(32):  # patterns cut from the text with <= k substitutions must be found
+            if offs[p] is not None and nsub[p] <= k:
+                assert whole[p] >= 1, p
+        plan.zero_counts()
+        cuts = [0, W // 3 + 1, (2 * W) // 3 + 7, W]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            plan.count_device(dev.data_ptr(), 0, n, n, a, b)
+        assert plan.read_counts() == whole
+        # sampled slices against the oracle: windows [a, a+L) of the global text
+        rng = np.random.default_rng(5)
+        L = 20000
+        starts = [0, W - L] + [int(x) for x in rng.integers(0, W - L, 3)]
+        starts += [int(o) - 50 for o in offs[:3] if o is not None and o > 50]
+        for a in starts:
+            plan.zero_counts()
+            plan.count_device(dev.data_ptr(), 0, n, n, a, a + L)
+            got = plan.read_counts()
+            seg_end = min(n, a + L + 63)
+            seg = oracle.synth_text(seed, a, seg_end - a).tobytes()
+            for p in (0, 1, 5, 13, 31):
+                if seg_end == n:  # slice touches the global end: tail truncation applies
+                    want = oracle.count_range(seg, pats[p], k, 0, L)
+                else:  # interior slice: pad so the oracle does not truncate at the slice end
+                    want = oracle.count_range(seg + b"\0" * 64, pats[p], k, 0, L)
+                assert got[p] == want, (a, p)

@@ -86,3 +86,15 @@ def test_live_against_reference_levenshtein():
     base = oracle.ref_count_matches(text, pats, 2, mode=0)
     assert oracle.ref_count_matches(text, pats, 2, mode=1, threads=4) == base
     assert oracle.ref_count_matches(text, pats, 2, mode=2, threads=4) == base
+
+
+def test_numpy_text_generator_equals_oracle_generator():
+    from apm_b200.synth import make_patterns, text_slice
+    for off, cnt in ((0, 257), (2**34 - 100, 100), (123456789, 4096)):
+        assert text_slice(0x5EED0001, off, cnt).tobytes() == oracle.synth_text(0x5EED0001, off, cnt).tobytes()
+    pats, offs, nsub = make_patterns(0x5EED0001, 1 << 20, 16, 64, 7)
+    assert len(pats) == 16 and all(len(p) == 64 for p in pats)
+    t = oracle.synth_text(0x5EED0001, offs[0], 64).tobytes()
+    assert pats[0] == t and nsub[0] == 0
+    t3 = oracle.synth_text(0x5EED0001, offs[3], 64).tobytes()
+    assert sum(a != b for a, b in zip(pats[3], t3)) == 3
