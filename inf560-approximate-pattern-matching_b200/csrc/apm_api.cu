@@ -59,6 +59,7 @@ struct Options {
     int mode = MODE_DIRECT;
     int rblock = 0;  // 0 = auto
     int tile = 0;    // 0 = auto
+    int variant = 0; // column-step code variant (see myers_step_fma)
     long long dp_scratch_mb = 256;
 };
 std::mutex g_opt_mu;
@@ -84,24 +85,32 @@ int device_ready(int *ndev) {
 
 // ---- kernel dispatch table ------------------------------------------------------------------------
 using MyersKernel = void (*)(const MyersArgs);
-template <int NW>
+template <int NW, int V>
 MyersKernel pick_r(int R) {
     switch (R) {
-        case 1: return myers_count_kernel<NW, 1>;
-        case 2: return myers_count_kernel<NW, 2>;
-        default: return myers_count_kernel<NW, 4>;
+        case 1: return myers_count_kernel<NW, 1, V>;
+        case 2: return myers_count_kernel<NW, 2, V>;
+        default: return myers_count_kernel<NW, 4, V>;
     }
 }
-MyersKernel pick_kernel(int NW, int R) {
+template <int V>
+MyersKernel pick_nw(int NW, int R) {
     switch (NW) {
-        case 1: return pick_r<1>(R);
-        case 2: return pick_r<2>(R);
-        case 3: return pick_r<3>(R);
-        case 4: return pick_r<4>(R);
-        case 5: return pick_r<5>(R);
-        case 6: return pick_r<6>(R);
-        case 7: return pick_r<7>(R);
-        default: return pick_r<8>(R);
+        case 1: return pick_r<1, V>(R);
+        case 2: return pick_r<2, V>(R);
+        case 3: return pick_r<3, V>(R);
+        case 4: return pick_r<4, V>(R);
+        case 5: return pick_r<5, V>(R);
+        case 6: return pick_r<6, V>(R);
+        case 7: return pick_r<7, V>(R);
+        default: return pick_r<8, V>(R);
+    }
+}
+MyersKernel pick_kernel(int NW, int R, int V) {
+    switch (V) {
+        case 0: return pick_nw<0>(NW, R);
+        case 1: return pick_nw<1>(NW, R);
+        default: return pick_nw<2>(NW, R);
     }
 }
 
@@ -192,7 +201,7 @@ int build_work(apm_plan *pl) {
         b.NW = NW;
         b.R = pl->opt.rblock ? pl->opt.rblock : auto_rblock(NW);
         b.EW = entry_words(b.R * NW);
-        b.fn = pick_kernel(NW, b.R);
+        b.fn = pick_kernel(NW, b.R, pl->opt.variant);
         b.mmin = (int)pl->pats[ids.front()].size();
         b.mmax = (int)pl->pats[ids.back()].size();
         size_t i = 0;
@@ -296,6 +305,8 @@ int launch_myers(apm_plan *pl, Bucket &b, const uint8_t *d_buf, long long buf_le
     a.mmax = b.mmax;
     a.k = pl->k;
     a.tile = tile;
+    a.c_one = 1u;
+    a.c_two = 2u;
     b.fn<<<dim3(gx, gy), kThreads, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     g_launches++;
@@ -435,6 +446,9 @@ int apm_set_option(const char *key, const char *value) {
             if (t < kThreads || t % kThreads || t > 16384) return bad();
             g_opt.tile = t;
         }
+    } else if (k == "variant") {
+        if (v == "0" || v == "1" || v == "2") g_opt.variant = atoi(value);
+        else return bad();
     } else if (k == "dp_scratch_mb") {
         long long mb = atoll(value);
         if (mb < 1 || mb > 65536) return bad();
@@ -455,6 +469,7 @@ const char *apm_get_option(const char *key) {
     else if (k == "mode") tl_optbuf = "direct";
     else if (k == "rblock") tl_optbuf = o.rblock ? std::to_string(o.rblock) : "auto";
     else if (k == "tile") tl_optbuf = o.tile ? std::to_string(o.tile) : "auto";
+    else if (k == "variant") tl_optbuf = std::to_string(o.variant);
     else if (k == "dp_scratch_mb") tl_optbuf = std::to_string(o.dp_scratch_mb);
     else return nullptr;
     return tl_optbuf.c_str();
@@ -631,7 +646,7 @@ int apm_int_peak(int kind, double *ops_per_sec, double *seconds) {
     int ndev = 0;
     int rc = device_ready(&ndev);
     if (rc) return rc;
-    if (kind < 0 || kind > 3 || !ops_per_sec) return fail(APM_EINVAL, "bad argument");
+    if (kind < 0 || kind > 9 || !ops_per_sec) return fail(APM_EINVAL, "bad argument");
     int dev = 0, sms = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -640,17 +655,18 @@ int apm_int_peak(int kind, double *ops_per_sec, double *seconds) {
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
-    const int iters = 4096, blocks = sms * 8;
-    const double ops_per_thread_iter = (kind == 0 || kind == 3) ? 2.0 * 8 * 8 : 1.0 * 8 * 8;
+    const int iters = kind == 9 ? 1024 : 4096, blocks = sms * 8;
+    const double ops_per_thread_iter = int_peak_ops_per_iter(kind);
     float best_ms = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {  // rep 0 = warm-up
         CUDA_TRY(cudaEventRecord(e0));
+#define APM_PEAK_CASE(K) case K: int_peak_kernel<K><<<blocks, 256>>>(d_out, iters, 0x9E3779B9u + rep, 0x7F4A7C15u); break;
         switch (kind) {
-            case 0: int_peak_kernel<0><<<blocks, 256>>>(d_out, iters, 0x9E3779B9u + rep, 0x7F4A7C15u); break;
-            case 1: int_peak_kernel<1><<<blocks, 256>>>(d_out, iters, 0x9E3779B9u + rep, 0x7F4A7C15u); break;
-            case 2: int_peak_kernel<2><<<blocks, 256>>>(d_out, iters, 0x9E3779B9u + rep, 0x7F4A7C15u); break;
-            default: int_peak_kernel<3><<<blocks, 256>>>(d_out, iters, 0x9E3779B9u + rep, 0x7F4A7C15u); break;
+            APM_PEAK_CASE(0) APM_PEAK_CASE(1) APM_PEAK_CASE(2) APM_PEAK_CASE(3) APM_PEAK_CASE(4)
+            APM_PEAK_CASE(5) APM_PEAK_CASE(6) APM_PEAK_CASE(7) APM_PEAK_CASE(8)
+            default: int_peak_kernel<9><<<blocks, 256>>>(d_out, iters, 0x9E3779B9u + rep, 0x7F4A7C15u); break;
         }
+#undef APM_PEAK_CASE
         CUDA_TRY(cudaGetLastError());
         g_launches++;
         CUDA_TRY(cudaEventRecord(e1));

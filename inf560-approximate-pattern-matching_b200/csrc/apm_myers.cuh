@@ -117,6 +117,93 @@ __host__ __device__ __forceinline__ void myers_step(uint32_t (&Pv)[NW], uint32_t
     }
 }
 
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// FMA-pipe variants of the column step.  On sm_100 LOP3/SHF/IADD3 issue on the ALU pipe (64 lanes/clk/SM)
+// and IMAD on the FMA pipe (another 64 lanes/clk/SM).  The 7 boolean instructions per word have to be
+// LOP3s, so the step is ALU-pipe bound; these variants move the three arithmetic instructions (the
+// carry add and the two 1-bit shifts, including the carries that cross 32-bit words) onto the FMA pipe:
+//   x << 1 | cin      ->  mad.lo (x, 2, cin)            carry out of a word = high half of mul.wide(x, 2)
+//   t + Pv            ->  mad.wide(t, 1, zext(Pv))      carry out of a word = high half of the product
+// The multipliers 1 and 2 come from kernel parameters so that ptxas cannot strength-reduce the IMADs
+// back into ALU-pipe shifts/adds.
+//   V = 1: shifts on the FMA pipe, multi-word (NW > 2) adds stay an IADD3.X chain
+//   V = 2: shifts and adds on the FMA pipe for every NW
+// ------------------------------------------------------------------------------------------------
+struct StepConst {
+    uint32_t one, two;  // 1 and 2
+    uint32_t estride;   // bytes per (group, code) Peq entry
+    uint64_t one64;     // 1 as a 64-bit value whose high half ptxas cannot prove to be zero
+};
+
+__device__ __forceinline__ uint32_t madlo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t madwide(uint32_t a, uint32_t b, uint64_t c) {
+    uint64_t d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mulwide(uint32_t a, uint32_t b) {
+    uint64_t d;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+template <int NW, int V>
+__device__ __forceinline__ void myers_step_fma(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[NW],
+                                               const StepConst &K) {
+    uint32_t s[NW];
+    if constexpr (NW == 1) {
+        s[0] = madlo(Eq[0] & Pv[0], K.one, Pv[0]);
+    } else if constexpr (V == 1 && NW > 2) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s[w] = Eq[w] & Pv[w];
+        add_chain<NW>(s, Pv);
+    } else {
+        uint32_t cin = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t t = Eq[w] & Pv[w];
+            if (w == NW - 1) {
+                s[w] = madlo(cin, K.one, madlo(t, K.one, Pv[w]));
+            } else {
+                // t + Pv (+ carry-in) as 64-bit values; every addend is the full result of a wide
+                // multiply, i.e. a natural register pair, so each line is a single IMAD.WIDE
+                uint64_t W = madwide(t, K.one, mulwide(Pv[w], K.one));
+                if (w > 0) W = madwide(cin, K.one, W);
+                s[w] = (uint32_t)W;
+                cin = (uint32_t)(W >> 32);
+            }
+        }
+    }
+    uint32_t cp = 0, cm = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const uint32_t Xv = Eq[w] | Mv[w];
+        const uint32_t Xh = (s[w] ^ Pv[w]) | Eq[w];
+        const uint32_t Ph = Mv[w] | ~(Xh | Pv[w]);
+        const uint32_t Mh = Pv[w] & Xh;
+        uint32_t Phs, Mhs;
+        if (w == NW - 1) {  // top word: no carry-out needed
+            Phs = madlo(Ph, K.two, w == 0 ? K.one : cp);
+            Mhs = w == 0 ? madlo(Mh, K.two, 0u) : madlo(Mh, K.two, cm);
+        } else {
+            const uint64_t Wp = w == 0 ? madwide(Ph, K.two, K.one64) : mulwide(Ph, K.two);
+            const uint64_t Wm = mulwide(Mh, K.two);
+            Phs = w == 0 ? (uint32_t)Wp : madlo(cp, K.one, (uint32_t)Wp);
+            Mhs = w == 0 ? (uint32_t)Wm : madlo(cm, K.one, (uint32_t)Wm);
+            cp = (uint32_t)(Wp >> 32);
+            cm = (uint32_t)(Wm >> 32);
+        }
+        Pv[w] = Mhs | ~(Xv | Phs);
+        Mv[w] = Phs & Xv;
+    }
+}
+#endif  // __CUDACC__
+
 // D[len][len] - len = sum of the vertical deltas of the last column over rows 1..len.
 template <int NW>
 __host__ __device__ __forceinline__ int myers_score_minus_len(const uint32_t (&Pv)[NW],
@@ -151,6 +238,7 @@ struct MyersArgs {
     int mmax;                    // largest m in this bucket
     int k;                       // approx_factor
     int tile;                    // window starts per tile (multiple of kThreads)
+    uint32_t c_one, c_two;       // the constants 1 and 2, opaque to ptxas (see myers_step_fma)
 };
 
 // Shared-memory layout (dynamic): see myers_smem_bytes() -- the host uses the same formula.
@@ -190,22 +278,28 @@ __device__ __forceinline__ void load_entry(const uint32_t *__restrict__ e, uint3
     for (int i = 0; i < N; ++i) dst[i] = tmp[i];
 }
 
-template <int NW, int R>
-__device__ __forceinline__ void advance_columns(const uint8_t *__restrict__ tp, const uint32_t *__restrict__ pq,
-                                                uint32_t (&Pv)[R][NW], uint32_t (&Mv)[R][NW]) {
+template <int NW, int R, int V>
+__device__ __forceinline__ void advance_columns(const uint8_t *__restrict__ tp, const unsigned char *__restrict__ sm,
+                                                uint32_t pq_off, uint32_t (&Pv)[R][NW], uint32_t (&Mv)[R][NW],
+                                                const StepConst &K) {
     constexpr int EW = entry_words(R * NW);
     const uint32_t c = *tp;
+    // byte offset of the (group, code) entry; V > 0 keeps this address computation on the FMA pipe too
+    const uint32_t off = V == 0 ? pq_off + c * (EW * 4u) : madlo(c, K.estride, pq_off);
     uint32_t Eq[R][NW];
-    load_entry<R * NW>(pq + c * EW, &Eq[0][0]);
+    load_entry<R * NW>(reinterpret_cast<const uint32_t *>(sm + off), &Eq[0][0]);
 #pragma unroll
-    for (int r = 0; r < R; ++r) myers_step<NW>(Pv[r], Mv[r], Eq[r]);
+    for (int r = 0; r < R; ++r) {
+        if constexpr (V == 0) myers_step<NW>(Pv[r], Mv[r], Eq[r]);
+        else myers_step_fma<NW, V>(Pv[r], Mv[r], Eq[r], K);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Persistent count kernel.  grid.x strides over text tiles, grid.y over pattern chunks; the host sizes
 // grid.x * grid.y to (#SMs x resident CTAs).
 // ------------------------------------------------------------------------------------------------
-template <int NW, int R>
+template <int NW, int R, int V>
 __global__ void __launch_bounds__(kThreads) myers_count_kernel(const MyersArgs a) {
     constexpr int EW = entry_words(R * NW);
     constexpr int U = 8;  // text symbols per unrolled inner-loop body
@@ -213,6 +307,7 @@ __global__ void __launch_bounds__(kThreads) myers_count_kernel(const MyersArgs a
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    const StepConst K = {a.c_one, a.c_two, (uint32_t)(EW * 4) * a.c_one, mulwide(a.c_one, a.c_one)};
     const size_t cap = myers_tile_cap(a.tile, a.mmax);
 
     // carve-up by integer offsets from the __shared__ array so every access stays an LDS/STS
@@ -333,7 +428,7 @@ __global__ void __launch_bounds__(kThreads) myers_count_kernel(const MyersArgs a
             for (int g = 0; g < gcount; ++g) {
                 const int m = s_gm[g];
                 const long long lim = min(tile_end, a.n_end - m + 1);  // full windows only
-                const uint32_t *pq = s_peq + (size_t)g * a.ncodes * EW;
+                const uint32_t pq = (uint32_t)off_peq + (uint32_t)g * (uint32_t)a.ncodes * (EW * 4u);  // byte offset
                 const int topbits = m - 32 * (NW - 1);
                 const uint32_t topmask = topbits >= 32 ? 0xFFFFFFFFu : ((1u << topbits) - 1u);
                 const int thresh = a.k - m;
@@ -355,10 +450,10 @@ __global__ void __launch_bounds__(kThreads) myers_count_kernel(const MyersArgs a
 #pragma unroll 1
                     for (; x + U <= m; x += U) {
 #pragma unroll
-                        for (int u = 0; u < U; ++u) advance_columns<NW, R>(tp + x + u, pq, Pv, Mv);
+                        for (int u = 0; u < U; ++u) advance_columns<NW, R, V>(tp + x + u, smem, pq, Pv, Mv, K);
                     }
 #pragma unroll 1
-                    for (; x < m; ++x) advance_columns<NW, R>(tp + x, pq, Pv, Mv);
+                    for (; x < m; ++x) advance_columns<NW, R, V>(tp + x, smem, pq, Pv, Mv, K);
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         const bool hit = valid && (myers_score_minus_len<NW>(Pv[r], Mv[r], topmask) <= thresh);

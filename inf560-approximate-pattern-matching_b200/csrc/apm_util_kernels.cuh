@@ -41,14 +41,19 @@ __global__ void __launch_bounds__(256) synth_text_kernel(uint8_t *out, unsigned 
 //   kind 1: lop3 only
 //   kind 2: add only   (ptxas may place some adds on the FMA pipe as IMAD.IADD)
 //   kind 3: lop3 + mad.lo alternating     (ALU pipe + FMA pipe together)
-// Every iteration executes 2*ILP integer instructions per thread for kinds 0 and 3, ILP otherwise.
+//   kind 4: mad.wide.u32 (IMAD.WIDE)  5: lop3 + mad.wide  6: mad.lo (IMAD)  7: mad.hi (IMAD.HI)
+//   kind 8: shf.l.wrap (SHF)          9: 7 lop3 : 3 mad.lo, the instruction mix of a one-word column step
 // ------------------------------------------------------------------------------------------------
 template <int KIND>
 __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters, uint32_t b, uint32_t c) {
     constexpr int ILP = 8;
     uint32_t a[ILP];
+    uint64_t a64[ILP];
 #pragma unroll
-    for (int i = 0; i < ILP; ++i) a[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x;
+    for (int i = 0; i < ILP; ++i) {
+        a[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x;
+        a64[i] = ((uint64_t)a[i] << 32) | (a[i] * 747796405u);
+    }
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -62,17 +67,49 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters,
                     asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
                 } else if constexpr (KIND == 2) {
                     asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(c));
-                } else {
+                } else if constexpr (KIND == 3) {
                     asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
                     asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                } else if constexpr (KIND == 4) {  // IMAD.WIDE.U32 with a live 64-bit addend
+                    asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a64[i]) : "r"(b), "r"(c));
+                } else if constexpr (KIND == 5) {  // LOP3 + IMAD.WIDE.U32
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+                    asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a64[i]) : "r"(a[i]), "r"(c));
+                } else if constexpr (KIND == 6) {  // IMAD only
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                } else if constexpr (KIND == 7) {  // IMAD.HI.U32 only
+                    asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                } else if constexpr (KIND == 8) {  // SHF funnel only
+                    asm volatile("shf.l.wrap.b32 %0, %0, %1, 1;" : "+r"(a[i]) : "r"(b));
+                } else {  // KIND 9: the NW=1 step mix, 7 LOP3 : 3 IMAD
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(a[i]) : "r"(b), "r"(c));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x1e;" : "+r"(a[i]) : "r"(b), "r"(c));
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(a[i]) : "r"(b), "r"(c));
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x1e;" : "+r"(a[i]) : "r"(b), "r"(c));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
                 }
             }
         }
     }
     uint32_t x = 0;
 #pragma unroll
-    for (int i = 0; i < ILP; ++i) x ^= a[i];
+    for (int i = 0; i < ILP; ++i) x ^= a[i] ^ (uint32_t)a64[i] ^ (uint32_t)(a64[i] >> 32);
     if (x == 0x12345678u) out[0] = x;  // practically never true; keeps the chains alive
+}
+
+// integer instructions per thread per loop iteration of int_peak_kernel<KIND>
+__host__ inline double int_peak_ops_per_iter(int kind) {
+    const double n = 8.0 * 8.0;  // rep x ILP
+    switch (kind) {
+        case 0: case 3: case 5: return 2 * n;
+        case 9: return 10 * n;
+        default: return n;
+    }
 }
 
 #endif  // __CUDACC__

@@ -19,7 +19,8 @@ CASES = cases()
 
 @pytest.fixture(autouse=True)
 def _default_options():
-    for k, v in (("kernel", "myers"), ("rblock", "auto"), ("tile", "auto"), ("gpus", "1"), ("shard", "auto")):
+    for k, v in (("kernel", "myers"), ("rblock", "auto"), ("tile", "auto"), ("gpus", "1"), ("shard", "auto"),
+                 ("variant", "0")):
         apm_b200.set_option(k, v)
     yield
 
@@ -54,6 +55,26 @@ def test_golden_every_register_blocking(name, rblock):
     case = next(c for c in CASES if c["name"] == name)
     apm_b200.set_option("rblock", rblock)
     assert apm_b200.count_matches(FX[case["text"]], case["patterns"], case["k"]) == case["expected"]
+
+
+@pytest.mark.parametrize("variant", ["1", "2"])
+@pytest.mark.parametrize("rblock", ["1", "2", "4"])
+@pytest.mark.parametrize("name", ["config1_readme", "x100_m64_k4", "small_m200_k10", "small_k2", "x100_k10"])
+def test_golden_every_step_variant(name, rblock, variant):
+    """The FMA-pipe formulations of the column step (myers_step_fma) are bit-identical."""
+    case = next(c for c in CASES if c["name"] == name)
+    apm_b200.set_option("rblock", rblock)
+    apm_b200.set_option("variant", variant)
+    assert apm_b200.count_matches(FX[case["text"]], case["patterns"], case["k"]) == case["expected"]
+
+
+@pytest.mark.parametrize("variant", ["1", "2"])
+@pytest.mark.parametrize("seed", range(12))
+def test_random_vs_oracle_step_variants(seed, variant):
+    rng = np.random.default_rng(7000 + seed)
+    text, pats, k = _random_case(rng)
+    apm_b200.set_option("variant", variant)
+    assert apm_b200.count_matches(text, pats, k) == oracle.count_matches(text, pats, k)
 
 
 def test_cli_drop_in(tmp_path):
