@@ -22,6 +22,7 @@
 #include "apm_common.cuh"
 #include "apm_dp.cuh"
 #include "apm_myers.cuh"
+#include "apm_sliced.cuh"
 #include "apm_util_kernels.cuh"
 
 using namespace apm;
@@ -49,13 +50,13 @@ int fail(int code, const char *fmt, ...) {
     } while (0)
 
 enum { SHARD_AUTO = 0, SHARD_DB = 1, SHARD_PATTERNS = 2 };
-enum { KERNEL_MYERS = 0, KERNEL_DP = 1 };
+enum { KERNEL_AUTO = 0, KERNEL_MYERS = 1, KERNEL_DP = 2, KERNEL_SLICED = 3 };
 enum { MODE_DIRECT = 0, MODE_FILTER = 1 };
 
 struct Options {
     int gpus = 1;  // 0 = all
     int shard = SHARD_AUTO;
-    int kernel = KERNEL_MYERS;
+    int kernel = KERNEL_AUTO;
     int mode = MODE_DIRECT;
     int rblock = 0;  // 0 = auto
     int tile = 0;    // 0 = auto
@@ -125,6 +126,16 @@ struct Bucket {
     int occ_cache_smem = -1, occ_cache = 0;
 };
 
+// patterns handled by the window-sliced kernel, one list per register-array size MC
+struct SlicedList {
+    int MC = 64, npat = 0, mmin = 0, mmax = 0;
+    std::vector<uint8_t> codes;  // [npat][MC]
+    std::vector<int> m, id;
+    uint8_t *d_codes = nullptr;
+    int *d_m = nullptr, *d_id = nullptr;
+    size_t smem_set = 0;
+};
+
 template <typename T>
 int upload(T **dptr, const std::vector<T> &h) {
     *dptr = nullptr;
@@ -143,6 +154,9 @@ struct apm_plan {
     uint8_t code_of[256];
     int shard_rank = 0, shard_world = 1;
     std::vector<Bucket> buckets;
+    std::vector<SlicedList> sliced;
+    int nplanes = 0;
+    uint8_t *d_plane_of = nullptr;
     std::vector<int> tail_list, all_list;
     int tail_width = 0, tail_mmax = 0, all_mmax = 0;
     uint8_t *d_code_of = nullptr, *d_pat_bytes = nullptr;
@@ -162,6 +176,12 @@ void free_work(apm_plan *pl) {
         cudaFree(b.d_group_pat);
     }
     pl->buckets.clear();
+    for (auto &l : pl->sliced) {
+        cudaFree(l.d_codes);
+        cudaFree(l.d_m);
+        cudaFree(l.d_id);
+    }
+    pl->sliced.clear();
     cudaFree(pl->d_tail_list);
     cudaFree(pl->d_all_list);
     pl->d_tail_list = pl->d_all_list = nullptr;
@@ -175,6 +195,7 @@ int auto_rblock(int NW) { return NW <= 2 ? 4 : (NW <= 4 ? 2 : 1); }
 int build_work(apm_plan *pl) {
     free_work(pl);
     std::vector<std::vector<int>> by_nw(kMaxWords + 1);
+    std::vector<int> sliced_ids[2];
     pl->tail_width = pl->tail_mmax = pl->all_mmax = 0;
     for (int p = 0; p < pl->P; ++p) {
         if (p % pl->shard_world != pl->shard_rank) continue;
@@ -184,7 +205,10 @@ int build_work(apm_plan *pl) {
             pl->all_mmax = std::max(pl->all_mmax, m);
             continue;
         }
-        by_nw[(m + 31) / 32].push_back(p);
+        const bool sliced_ok = m <= 64 && pl->nplanes <= kSlicedMaxPlanes &&
+                               (pl->opt.kernel == KERNEL_SLICED || pl->opt.kernel == KERNEL_AUTO);
+        if (sliced_ok) sliced_ids[m <= 32 ? 0 : 1].push_back(p);
+        else by_nw[(m + 31) / 32].push_back(p);
         const int tw = m - 1 - pl->k;  // number of truncated tail windows (sequential.c:121,131-134)
         if (tw > 0) {
             pl->tail_list.push_back(p);
@@ -230,6 +254,29 @@ int build_work(apm_plan *pl) {
         if ((rc = upload(&b.d_group_m, b.group_m))) return rc;
         if ((rc = upload(&b.d_group_pat, b.group_pat))) return rc;
         pl->buckets.push_back(std::move(b));
+    }
+    for (int which = 0; which < 2; ++which) {
+        auto &ids = sliced_ids[which];
+        if (ids.empty()) continue;
+        std::stable_sort(ids.begin(), ids.end(),
+                         [&](int a, int b) { return pl->pats[a].size() < pl->pats[b].size(); });
+        SlicedList l;
+        l.MC = which == 0 ? 32 : 64;
+        l.npat = (int)ids.size();
+        l.mmin = (int)pl->pats[ids.front()].size();
+        l.mmax = (int)pl->pats[ids.back()].size();
+        l.codes.assign((size_t)l.npat * l.MC, 0);
+        for (int i = 0; i < l.npat; ++i) {
+            const std::string &s = pl->pats[ids[i]];
+            for (size_t x = 0; x < s.size(); ++x) l.codes[(size_t)i * l.MC + x] = pl->code_of[(uint8_t)s[x]];
+            l.m.push_back((int)s.size());
+            l.id.push_back(ids[i]);
+        }
+        int rc2;
+        if ((rc2 = upload(&l.d_codes, l.codes))) return rc2;
+        if ((rc2 = upload(&l.d_m, l.m))) return rc2;
+        if ((rc2 = upload(&l.d_id, l.id))) return rc2;
+        pl->sliced.push_back(std::move(l));
     }
     int rc;
     if ((rc = upload(&pl->d_tail_list, pl->tail_list))) return rc;
@@ -311,6 +358,61 @@ int launch_myers(apm_plan *pl, Bucket &b, const uint8_t *d_buf, long long buf_le
     CUDA_TRY(cudaGetLastError());
     g_launches++;
     return APM_OK;
+}
+
+template <int MC>
+int launch_sliced_mc(apm_plan *pl, SlicedList &l, const SlicedArgs &base, long long nwin, cudaStream_t st) {
+    auto fn = sliced_count_kernel<MC>;
+    const long long ntiles = (nwin + kSlicedTile - 1) / kSlicedTile;
+    int ppc = std::min(l.npat, 128);
+    size_t smem = sliced_smem_bytes<MC>(ppc, pl->nplanes);
+    if (smem > l.smem_set) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        l.smem_set = smem;
+    }
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kSlicedThreads, smem));
+    if (occ < 1) return fail(APM_ECUDA, "sliced kernel MC=%d does not fit an SM (smem %zu)", MC, smem);
+    const long long capacity = (long long)pl->num_sms * occ;
+    unsigned gx, gy = 1;
+    if (ntiles >= capacity) {
+        gx = (unsigned)capacity;
+    } else {
+        gx = (unsigned)ntiles;
+        const long long want_y = std::min<long long>(l.npat, (capacity + ntiles - 1) / ntiles);
+        ppc = std::min(ppc, (int)((l.npat + want_y - 1) / want_y));
+        const int nchunks = (l.npat + ppc - 1) / ppc;
+        gy = (unsigned)std::min<long long>(want_y, nchunks);
+        smem = sliced_smem_bytes<MC>(ppc, pl->nplanes);
+    }
+    SlicedArgs a = base;
+    a.pats_per_chunk = ppc;
+    fn<<<dim3(gx, gy), kSlicedThreads, smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    g_launches++;
+    return APM_OK;
+}
+
+int launch_sliced(apm_plan *pl, SlicedList &l, const uint8_t *d_buf, long long buf_len, long long n_end, long long w0,
+                  long long w1, cudaStream_t st) {
+    const long long lim = std::min(w1, n_end - l.mmin + 1);
+    if (lim <= w0) return APM_OK;
+    SlicedArgs a;
+    a.buf = d_buf;
+    a.buf_len = buf_len;
+    a.n_end = n_end;
+    a.w0 = w0;
+    a.w1 = lim;
+    a.pat_codes = l.d_codes;
+    a.pat_m = l.d_m;
+    a.pat_id = l.d_id;
+    a.plane_of = pl->d_plane_of;
+    a.counts = pl->d_counts;
+    a.npat = l.npat;
+    a.pats_per_chunk = 0;
+    a.nplanes = pl->nplanes;
+    a.k = pl->k;
+    return l.MC == 32 ? launch_sliced_mc<32>(pl, l, a, lim - w0, st) : launch_sliced_mc<64>(pl, l, a, lim - w0, st);
 }
 
 int launch_dp(apm_plan *pl, const uint8_t *d_buf, long long buf_offset, long long n_total, long long j_begin,
@@ -429,7 +531,9 @@ int apm_set_option(const char *key, const char *value) {
         else if (v == "patterns" || v == "PATTERNS_OVER_RANKS") g_opt.shard = SHARD_PATTERNS;
         else return bad();
     } else if (k == "kernel") {
-        if (v == "myers") g_opt.kernel = KERNEL_MYERS;
+        if (v == "auto") g_opt.kernel = KERNEL_AUTO;
+        else if (v == "myers" || v == "rows") g_opt.kernel = KERNEL_MYERS;
+        else if (v == "sliced") g_opt.kernel = KERNEL_SLICED;
         else if (v == "dp") g_opt.kernel = KERNEL_DP;
         else return bad();
     } else if (k == "mode") {
@@ -465,7 +569,8 @@ const char *apm_get_option(const char *key) {
     const std::string k = key;
     if (k == "gpus") tl_optbuf = o.gpus ? std::to_string(o.gpus) : "all";
     else if (k == "shard") tl_optbuf = o.shard == SHARD_DB ? "db" : (o.shard == SHARD_PATTERNS ? "patterns" : "auto");
-    else if (k == "kernel") tl_optbuf = o.kernel == KERNEL_DP ? "dp" : "myers";
+    else if (k == "kernel")
+        tl_optbuf = o.kernel == KERNEL_DP ? "dp" : (o.kernel == KERNEL_MYERS ? "myers" : (o.kernel == KERNEL_SLICED ? "sliced" : "auto"));
     else if (k == "mode") tl_optbuf = "direct";
     else if (k == "rblock") tl_optbuf = o.rblock ? std::to_string(o.rblock) : "auto";
     else if (k == "tile") tl_optbuf = o.tile ? std::to_string(o.tile) : "auto";
@@ -525,6 +630,10 @@ int apm_plan_create(const char *const *patterns, const int *pattern_len, int nb_
     };
     std::vector<uint8_t> map(pl->code_of, pl->code_of + 256);
     if ((rc = upload(&pl->d_code_of, map))) return cleanup_fail(rc);
+    pl->nplanes = A;  // one occurrence plane per pattern symbol (window-sliced kernel)
+    std::vector<uint8_t> planes(256);
+    for (int b = 0; b < 256; ++b) planes[b] = used[b] ? pl->code_of[b] : kNoPlane;
+    if ((rc = upload(&pl->d_plane_of, planes))) return cleanup_fail(rc);
     if ((rc = upload(&pl->d_pat_bytes, flat))) return cleanup_fail(rc);
     if ((rc = upload(&pl->d_pat_off, off))) return cleanup_fail(rc);
     if ((rc = upload(&pl->d_pat_len, len))) return cleanup_fail(rc);
@@ -546,6 +655,7 @@ int apm_plan_destroy(apm_plan *pl) {
     cudaSetDevice(pl->device);
     free_work(pl);
     cudaFree(pl->d_code_of);
+    cudaFree(pl->d_plane_of);
     cudaFree(pl->d_pat_bytes);
     cudaFree(pl->d_pat_off);
     cudaFree(pl->d_pat_len);
@@ -620,6 +730,11 @@ int apm_plan_count_device(apm_plan *pl, const unsigned char *d_buf, unsigned lon
         rc = launch_myers(pl, b, d_buf, (long long)buf_len, N - (long long)buf_offset, jb - (long long)buf_offset,
                           je - (long long)buf_offset, st);
         if (rc) break;
+    }
+    for (auto &l : pl->sliced) {
+        if (rc) break;
+        rc = launch_sliced(pl, l, d_buf, (long long)buf_len, N - (long long)buf_offset, jb - (long long)buf_offset,
+                           je - (long long)buf_offset, st);
     }
     if (!rc) rc = launch_dp(pl, d_buf, (long long)buf_offset, N, jb, je, st);
     if (cur != pl->device) cudaSetDevice(cur);

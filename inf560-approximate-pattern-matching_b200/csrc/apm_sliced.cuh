@@ -1,0 +1,299 @@
+// apm_sliced.cuh -- window-sliced bit-parallel kernel: the same DP as src/utils.c:76-99, every one of the
+// m x m cells evaluated, but with the 32 bits of a register holding the SAME cell of 32 CONSECUTIVE WINDOWS
+// (bit b <-> window start j0 + b) instead of 32 rows of one window.
+//
+// Why: in the row-parallel (Hyyro/Myers) formulation of apm_myers.cuh a column step costs 7 boolean
+// instructions + 1 carry add + 2 shifts per 32 cells, and on sm_100 it is bound by the ALU pipe (LOP3/SHF
+// /IADD3 with carry: 64 lanes/clk/SM); the cross-word carries of m > 32 add more ALU work.  Slicing across
+// windows makes every cell's recurrence purely boolean -- no adder, no shifts, no carries between words:
+//
+//   a = D[i][j-1]-D[i-1][j-1] (vertical delta, left neighbour)    b = D[i-1][j]-D[i-1][j-1] (horizontal, above)
+//   d0 = eq | a- | b-                      diagonal step is 0
+//   v+ = b- | ~(d0 | b+)   v- = b+ & d0    vertical delta of this cell   (goes right)
+//   h+ = a- | ~(d0 | a+)   h- = a+ & d0    horizontal delta of this cell (goes down)
+//
+// = 5 LOP3 per cell per 32 windows (0.156 instructions per DP cell, vs >= 0.27 ALU-pipe instructions per cell
+// for the row-parallel step), identical for every pattern length.  These are Myers' delta equations applied
+// per cell; the boundary D[0][j] = j, D[i][0] = i (utils.c:84-88) is "+1" in both directions.
+//
+// Mapping
+//   thread t of a CTA  <-> the 32 windows starting at tile_start + 32 t
+//   match bits         <-> eq(i, j) for those 32 windows is bits [32t + j-1, +32) of the occurrence bit-vector
+//                          of symbol P[i-1] in the text tile.  All 32-bit windows of those bit-vectors are
+//                          precomputed once per tile into shared memory (U table, one plane per symbol),
+//                          laid out so that the 32 lanes of a warp read conflict-free with LDS.64 and an
+//                          immediate offset per column.
+//   state              <-> the horizontal deltas of the previous row for all MC columns live in 2*MC
+//                          registers; the sweep is row-major (pattern symbol outer, text column inner), so
+//                          the plane of the row's symbol is selected once per row.
+//   distance           <-> D[m][m] = m + sum_j (h+ - h-) of the last row: a carry-save adder tree over the
+//                          bit-planes (Harley-Seal), then a bit-sliced compare with the threshold.
+//   text tile          <-> same TMA 1-D bulk staging + re-coding as the row-parallel kernel (apm_tile.cuh).
+#pragma once
+#include "apm_common.cuh"
+#include "apm_tile.cuh"
+
+namespace apm {
+
+constexpr int kSlicedThreads = 128;
+constexpr int kSlicedTile = 32 * kSlicedThreads;  // window starts per tile
+constexpr int kURowBytes = 136;                   // 34 words per U row: lanes hit distinct banks with LDS.64
+constexpr int kSlicedMaxPlanes = 8;               // symbols with their own occurrence plane
+constexpr uint8_t kNoPlane = 0xFF;
+
+#ifdef __CUDACC__
+
+struct SlicedArgs {
+    const uint8_t *buf;          // device text; buf[0] is global byte buf_offset
+    long long buf_len, n_end;    // valid bytes; local index of the global end of text
+    long long w0, w1;            // local window-start range
+    const uint8_t *pat_codes;    // [npat][MC] plane index of every pattern symbol (padded)
+    const int *pat_m;            // [npat]
+    const int *pat_id;           // [npat] index into counts
+    const uint8_t *plane_of;     // [256] byte -> plane index or kNoPlane
+    unsigned long long *counts;
+    int npat, pats_per_chunk, nplanes, k;
+};
+
+// geometry shared by host and device
+__host__ __device__ constexpr int sliced_rowsU(int MC) { return kSlicedTile / 32 + MC / 32 + 1; }  // rows per U plane
+__host__ __device__ constexpr int sliced_nB(int MC) { return sliced_rowsU(MC) + 1; }  // words per bit-vector
+__host__ __device__ constexpr int sliced_span(int MC) { return (sliced_nB(MC) * 32 + 15 + 3) / 4 * 4; }  // bytes re-coded
+__host__ __device__ constexpr size_t sliced_cap(int MC) { return (size_t)(sliced_span(MC) + 15) / 16 * 16 + 16; }
+
+template <int MC>
+__host__ __device__ inline size_t sliced_smem_bytes(int pats_per_chunk, int nplanes) {
+    size_t b = 64 + 256 + 3 * sliced_cap(MC);
+    b += (size_t)nplanes * sliced_nB(MC) * 4;
+    b = (b + 15) / 16 * 16;
+    b += (size_t)nplanes * sliced_rowsU(MC) * kURowBytes;
+    b += (size_t)pats_per_chunk * (MC + 3 * sizeof(int));
+    return b + 32;
+}
+
+// one LOP3: any boolean function of three words, LUT evaluated on a = 0xF0, b = 0xCC, c = 0xAA.
+// Written as PTX so that the five-instruction decomposition of a cell is exactly what gets executed
+// (left to itself the compiler re-associates the expressions into six LOP3s per cell).
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+constexpr int kLutOr3 = 0xFE;        // a | b | c
+constexpr int kLutAndOr = 0xE0;      // a & (b | c)
+constexpr int kLutOrNor = 0xF1;      // a | ~(b | c)
+
+// full adder on bit-planes: a <- a ^ b ^ c, returns majority(a, b, c)   (2 LOP3)
+__device__ __forceinline__ uint32_t plane_fa(uint32_t &a, uint32_t b, uint32_t c) {
+    const uint32_t carry = (a & b) | (c & (a | b));
+    a = a ^ b ^ c;
+    return carry;
+}
+
+// Harley-Seal style accumulation: acc[l] holds the weight-2^l plane of the running sum, pend[l] a pending
+// carry of the same weight.  IDX is the (compile-time) index of the pair being pushed.
+template <int L, int IDX, int NL>
+struct PushCarry {
+    static __device__ __forceinline__ void run(uint32_t (&acc)[NL], uint32_t (&pend)[NL], uint32_t c) {
+        if constexpr (IDX & 1) {
+            const uint32_t c2 = plane_fa(acc[L], pend[L], c);
+            PushCarry<L + 1, (IDX >> 1), NL>::run(acc, pend, c2);
+        } else {
+            pend[L] = c;
+        }
+    }
+};
+
+template <int MC, int I, int NL>
+struct SumPlanes {  // adds the planes of columns 2I and 2I+1 (h+ and ~h- of each), recursion over I
+    static __device__ __forceinline__ void run(const uint32_t (&hp)[MC], const uint32_t (&hm)[MC], uint32_t (&acc)[NL],
+                                               uint32_t (&pend)[NL]) {
+        if constexpr (I < MC) {
+            // pair index 2I: (h+[I], ~h-[I]) ; the second pair of this step comes from column I+1
+            const uint32_t c = plane_fa(acc[0], hp[I], ~hm[I]);
+            PushCarry<1, I, NL>::run(acc, pend, c);
+            SumPlanes<MC, I + 1, NL>::run(hp, hm, acc, pend);
+        }
+    }
+};
+
+template <int MC>
+__global__ void __launch_bounds__(kSlicedThreads) sliced_count_kernel(const SlicedArgs a) {
+    static_assert(MC == 32 || MC == 64, "MC must be 32 or 64");
+    constexpr int LOG = MC == 32 ? 6 : 7;  // 2*MC planes are summed: value range [0, 2*MC]
+    constexpr int NL = LOG + 1;
+    constexpr int CH = 8;                  // columns per uniform early-exit check
+    extern __shared__ __align__(128) unsigned char smem[];
+
+    const int tid = threadIdx.x;
+    constexpr size_t cap = sliced_cap(MC);
+    constexpr int nB = sliced_nB(MC);        // words per occurrence bit-vector
+    constexpr int rowsU = sliced_rowsU(MC);  // rows per U plane
+    const size_t off_raw = 64 + 256;
+    const size_t off_codes = off_raw + 2 * cap;
+    const size_t off_B = off_codes + cap;
+    const size_t off_U = (off_B + (size_t)a.nplanes * nB * 4 + 15) & ~size_t(15);
+    const size_t off_pc = off_U + (size_t)a.nplanes * rowsU * kURowBytes;
+    const size_t off_pm = off_pc + (size_t)a.pats_per_chunk * MC;
+    const size_t off_pid = off_pm + sizeof(int) * a.pats_per_chunk;
+    const size_t off_cnt = off_pid + sizeof(int) * a.pats_per_chunk;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+    uint8_t *s_map = smem + 64;
+    uint8_t *s_raw0 = smem + off_raw;
+    uint8_t *s_codes = smem + off_codes;
+    uint32_t *s_B = reinterpret_cast<uint32_t *>(smem + off_B);
+    uint8_t *s_pc = smem + off_pc;
+    int *s_pm = reinterpret_cast<int *>(smem + off_pm);
+    int *s_pid = reinterpret_cast<int *>(smem + off_pid);
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + off_cnt);
+    const uint32_t plane_bytes = rowsU * kURowBytes;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < 256; i += kSlicedThreads) s_map[i] = a.plane_of[i];
+    __syncthreads();
+
+    const long long nwin = a.w1 - a.w0;
+    const long long ntiles = (nwin + kSlicedTile - 1) / kSlicedTile;
+    constexpr int span = sliced_span(MC);  // bytes re-coded per tile (<= cap)
+    uint32_t phase = 0;
+
+    const int nchunks = (a.npat + a.pats_per_chunk - 1) / a.pats_per_chunk;
+    for (int chunk = blockIdx.y; chunk < nchunks; chunk += gridDim.y) {
+        const int p0 = chunk * a.pats_per_chunk;
+        const int pcount = min(a.pats_per_chunk, a.npat - p0);
+        for (int i = tid; i < pcount * MC; i += kSlicedThreads) s_pc[i] = a.pat_codes[(size_t)p0 * MC + i];
+        for (int i = tid; i < pcount; i += kSlicedThreads) {
+            s_pm[i] = a.pat_m[p0 + i];
+            s_pid[i] = a.pat_id[p0 + i];
+            s_cnt[i] = 0;
+        }
+        int stage = 0;
+        long long t = blockIdx.x;
+        if (tid == 0 && t < ntiles)
+            tile_issue(tile_geometry(a.buf, a.buf_len, a.w0, t, kSlicedTile, MC), a.buf, s_raw0, &bars[0]);
+        __syncthreads();
+
+        for (; t < ntiles; t += gridDim.x) {
+            const long long tn = t + gridDim.x;
+            if (tid == 0 && tn < ntiles)
+                tile_issue(tile_geometry(a.buf, a.buf_len, a.w0, tn, kSlicedTile, MC), a.buf,
+                           s_raw0 + (stage ^ 1) * cap, &bars[stage ^ 1]);
+            const TileGeom g = tile_geometry(a.buf, a.buf_len, a.w0, t, kSlicedTile, MC);
+            if (g.tb > g.ta) {
+                mbar_wait(&bars[stage], (phase >> stage) & 1u);
+                phase ^= (1u << stage);
+            }
+            tile_encode(g, a.buf, a.buf_len, s_raw0 + stage * cap, s_map, kNoPlane, s_codes, span, tid,
+                        kSlicedThreads);
+            __syncthreads();
+            // ---- occurrence bit-vectors: bit x of B[p] <-> text position ts + x holds the symbol of plane p
+            {
+                const uint8_t *tc = s_codes + (g.ts - g.a0);
+                const int lane = tid & 31;
+                for (int w = tid >> 5; w < nB; w += kSlicedThreads / 32) {
+                    const uint32_t c = tc[32 * w + lane];
+                    for (int p = 0; p < a.nplanes; ++p) {
+                        const uint32_t bits = __ballot_sync(0xFFFFFFFFu, c == (uint32_t)p);
+                        if (lane == 0) s_B[p * nB + w] = bits;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- U table: U[p][w][s] = bits [32 w + s, +32) of B[p]
+            for (int idx = tid; idx < a.nplanes * rowsU; idx += kSlicedThreads) {
+                const int p = idx / rowsU, w = idx - p * rowsU;
+                const uint32_t lo = s_B[p * nB + w], hi = s_B[p * nB + w + 1];
+                uint32_t *dst = reinterpret_cast<uint32_t *>(smem + off_U + (size_t)p * plane_bytes + (size_t)w * kURowBytes);
+#pragma unroll
+                for (int s = 0; s < 32; ++s) dst[s] = __funnelshift_r(lo, hi, s);
+            }
+            __syncthreads();
+
+            // ---- hot loop: patterns x rows x columns, 5 LOP3 per cell
+            const long long tile_end = min(g.ts + (long long)kSlicedTile, a.w1);
+            const long long jbase = g.ts + 32ll * tid;
+            const unsigned char *urow = smem + off_U + (size_t)tid * kURowBytes;
+            for (int pi = 0; pi < pcount; ++pi) {
+                const int m = s_pm[pi];
+                const long long lim = min(tile_end, a.n_end - m + 1);  // full windows only
+                const long long nvalid = lim - jbase;
+                const uint32_t validmask = nvalid >= 32 ? 0xFFFFFFFFu : (nvalid <= 0 ? 0u : ((1u << (int)nvalid) - 1u));
+                uint32_t hits = 0;
+                if (validmask != 0u) {
+                    uint32_t hp[MC], hm[MC];
+#pragma unroll
+                    for (int j = 0; j < MC; ++j) { hp[j] = 0xFFFFFFFFu; hm[j] = 0u; }  // D[0][j] - D[0][j-1] = +1
+                    const uint8_t *pc = s_pc + pi * MC;
+#pragma unroll 1
+                    for (int i = 0; i < m; ++i) {
+                        const unsigned char *e = urow + (uint32_t)pc[i] * plane_bytes;
+                        uint32_t ap = 0xFFFFFFFFu, am = 0u;  // D[i][0] - D[i-1][0] = +1
+#pragma unroll
+                        for (int c = 0; c < MC; c += 2) {
+                            if ((c % CH) == 0 && c >= m) break;  // uniform: m is the same for the whole CTA
+                            const uint2 eq = *reinterpret_cast<const uint2 *>(e + (c >> 5) * kURowBytes + (c & 31) * 4);
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t q = h ? eq.y : eq.x;
+                                const uint32_t bp = hp[c + h], bm = hm[c + h];
+                                // a+ & a- = 0 and b+ & b- = 0, so b+ & d0 = b+ & (eq | a-): the chain
+                                // a- -> a-' that links a cell to its right neighbour is one LOP3 deep
+                                const uint32_t d0 = lop3<kLutOr3>(q, am, bm);
+                                const uint32_t vm = lop3<kLutAndOr>(bp, q, am);
+                                const uint32_t vp = lop3<kLutOrNor>(bm, d0, bp);
+                                hp[c + h] = lop3<kLutOrNor>(am, d0, ap);
+                                hm[c + h] = lop3<kLutAndOr>(ap, q, bm);
+                                ap = vp;
+                                am = vm;
+                            }
+                        }
+                    }
+                    if (m != MC) {  // columns >= m: back to the neutral boundary value so they add a constant
+#pragma unroll
+                        for (int j = 0; j < MC; ++j)
+                            if (j >= m) { hp[j] = 0xFFFFFFFFu; hm[j] = 0u; }
+                    }
+                    // V = sum_j (h+[j] + ~h-[j]) = D[m][m] + 2 (MC - m), bit-sliced in acc[0..LOG-1] + pend[LOG]
+                    uint32_t acc[NL], pend[NL];
+#pragma unroll
+                    for (int l = 0; l < NL; ++l) { acc[l] = 0u; pend[l] = 0u; }
+                    SumPlanes<MC, 0, NL>::run(hp, hm, acc, pend);
+                    acc[LOG] = pend[LOG];
+                    // windows with V <= T
+                    const int T = a.k + 2 * (MC - m);
+                    uint32_t le;
+                    if (T >= 2 * MC) le = 0xFFFFFFFFu;
+                    else {
+                        uint32_t lt = 0u, eqm = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int l = LOG; l >= 0; --l) {
+                            const uint32_t tb = ((T >> l) & 1) ? 0xFFFFFFFFu : 0u;
+                            lt |= eqm & ~acc[l] & tb;
+                            eqm &= ~(acc[l] ^ tb);
+                        }
+                        le = lt | eqm;
+                    }
+                    hits = __popc(le & validmask);
+                }
+                hits = __reduce_add_sync(0xFFFFFFFFu, hits);
+                if ((tid & 31) == 0 && hits) atomicAdd(&s_cnt[pi], hits);
+            }
+            __syncthreads();  // U, codes, raw[stage] free for reuse
+            stage ^= 1;
+        }
+        for (int i = tid; i < pcount; i += kSlicedThreads) {
+            const uint32_t c = s_cnt[i];
+            if (c) atomicAdd(&a.counts[s_pid[i]], (unsigned long long)c);
+        }
+        __syncthreads();
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace apm

@@ -47,7 +47,9 @@ def test_product_does_not_reference_the_oracle():
 def test_option_validation():
     apm_b200.set_option("kernel", "dp")
     assert apm_b200.get_option("kernel") == "dp"
-    apm_b200.set_option("kernel", "myers")
+    apm_b200.set_option("kernel", "sliced")
+    assert apm_b200.get_option("kernel") == "sliced"
+    apm_b200.set_option("kernel", "auto")
     apm_b200.set_option("shard", "DB_OVER_RANKS")
     assert apm_b200.get_option("shard") == "db"
     apm_b200.set_option("shard", "auto")

@@ -19,7 +19,7 @@ CASES = cases()
 
 @pytest.fixture(autouse=True)
 def _default_options():
-    for k, v in (("kernel", "myers"), ("rblock", "auto"), ("tile", "auto"), ("gpus", "1"), ("shard", "auto"),
+    for k, v in (("kernel", "auto"), ("rblock", "auto"), ("tile", "auto"), ("gpus", "1"), ("shard", "auto"),
                  ("variant", "0")):
         apm_b200.set_option(k, v)
     yield
@@ -33,8 +33,11 @@ def _torch():
 # ---------------------------------------------------------------------------------------------
 # golden vectors (reference apm_sequential outputs)
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", ["auto", "myers", "sliced"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: c["name"])
-def test_golden_host_api(case):
+def test_golden_host_api(case, kernel):
+    """auto = window-sliced kernel for m <= 64 / small alphabets, row-parallel Myers kernel otherwise."""
+    apm_b200.set_option("kernel", kernel)
     before = apm_b200.launch_count()
     got = apm_b200.count_matches(FX[case["text"]], case["patterns"], case["k"])
     assert got == case["expected"]
@@ -53,6 +56,7 @@ def test_golden_dp_kernel(name):
 @pytest.mark.parametrize("name", ["config1_readme", "x100_m64_k4", "small_m200_k10", "small_k2"])
 def test_golden_every_register_blocking(name, rblock):
     case = next(c for c in CASES if c["name"] == name)
+    apm_b200.set_option("kernel", "myers")
     apm_b200.set_option("rblock", rblock)
     assert apm_b200.count_matches(FX[case["text"]], case["patterns"], case["k"]) == case["expected"]
 
@@ -63,6 +67,7 @@ def test_golden_every_register_blocking(name, rblock):
 def test_golden_every_step_variant(name, rblock, variant):
     """The FMA-pipe formulations of the column step (myers_step_fma) are bit-identical."""
     case = next(c for c in CASES if c["name"] == name)
+    apm_b200.set_option("kernel", "myers")
     apm_b200.set_option("rblock", rblock)
     apm_b200.set_option("variant", variant)
     assert apm_b200.count_matches(FX[case["text"]], case["patterns"], case["k"]) == case["expected"]
@@ -73,6 +78,7 @@ def test_golden_every_step_variant(name, rblock, variant):
 def test_random_vs_oracle_step_variants(seed, variant):
     rng = np.random.default_rng(7000 + seed)
     text, pats, k = _random_case(rng)
+    apm_b200.set_option("kernel", "myers")
     apm_b200.set_option("variant", variant)
     assert apm_b200.count_matches(text, pats, k) == oracle.count_matches(text, pats, k)
 
@@ -125,7 +131,7 @@ EDGE = [
 
 
 @pytest.mark.parametrize("idx", range(len(EDGE)))
-@pytest.mark.parametrize("kernel", ["myers", "dp"])
+@pytest.mark.parametrize("kernel", ["auto", "myers", "dp"])
 def test_edge_cases(idx, kernel):
     text, pats, k = EDGE[idx]
     apm_b200.set_option("kernel", kernel)
@@ -166,10 +172,12 @@ def _random_case(rng, max_n=3000):
     return text, pats, k
 
 
+@pytest.mark.parametrize("kernel", ["auto", "myers"])
 @pytest.mark.parametrize("seed", range(40))
-def test_random_vs_oracle(seed):
+def test_random_vs_oracle(seed, kernel):
     rng = np.random.default_rng(1000 + seed)
     text, pats, k = _random_case(rng)
+    apm_b200.set_option("kernel", kernel)
     assert apm_b200.count_matches(text, pats, k) == oracle.count_matches(text, pats, k)
 
 
@@ -180,8 +188,9 @@ def test_myers_vs_dp_kernel_large_slice():
     k = 6
     apm_b200.set_option("kernel", "dp")
     dp = apm_b200.count_matches(text, pats, k)
-    apm_b200.set_option("kernel", "myers")
-    assert apm_b200.count_matches(text, pats, k) == dp
+    for kernel in ("myers", "sliced", "auto"):
+        apm_b200.set_option("kernel", kernel)
+        assert apm_b200.count_matches(text, pats, k) == dp, kernel
 
 
 # ---------------------------------------------------------------------------------------------
@@ -197,8 +206,9 @@ def test_synth_text_device_matches_oracle_generator():
         assert got == oracle.synth_text(0x5EED0001, off, cnt).tobytes()
 
 
+@pytest.mark.parametrize("kernel", ["auto", "myers"])
 @pytest.mark.parametrize("nshards,misalign", [(1, 0), (2, 1), (3, 5), (7, 15), (8, 0)])
-def test_db_shards_with_halo_are_exact(nshards, misalign):
+def test_db_shards_with_halo_are_exact(nshards, misalign, kernel):
     """Sum over shards == unsharded; each shard sees only its own bytes + (m_max-1)-byte halo, at an
     arbitrary (unaligned) device address; seams fall on / next to planted matches."""
     torch = _torch()
@@ -215,6 +225,7 @@ def test_db_shards_with_halo_are_exact(nshards, misalign):
     k = 3
     want = oracle.count_matches(text, pats, k)
     W = n - k
+    apm_b200.set_option("kernel", kernel)
     with apm_b200.Plan(pats, k) as plan:
         for g in range(nshards):
             j0, j1 = W * g // nshards, W * (g + 1) // nshards
@@ -254,6 +265,7 @@ def test_pattern_shards_sum_to_whole(world):
 @pytest.mark.parametrize("tile", ["256", "512", "2048", "4096"])
 def test_tile_sizes(tile):
     case = next(c for c in CASES if c["name"] == "x100_k5")
+    apm_b200.set_option("kernel", "myers")
     apm_b200.set_option("tile", tile)
     assert apm_b200.count_matches(FX[case["text"]], case["patterns"], case["k"]) == case["expected"]
 
@@ -276,7 +288,8 @@ def test_counts_accumulate_and_zero():
 # ---------------------------------------------------------------------------------------------
 # BASELINE-sized inputs: size-independent properties + sampled-slice oracle
 # ---------------------------------------------------------------------------------------------
-def test_large_synthetic_sampled_slices():
+@pytest.mark.parametrize("kernel", ["auto", "myers"])
+def test_large_synthetic_sampled_slices(kernel):
     """64 MiB of the config-3 text, 32 patterns of length 64, k = 4: per-slice counts equal the oracle's
     on random slices + the tail slice; planted patterns are found; sharding does not change anything."""
     torch = _torch()
@@ -288,6 +301,7 @@ def test_large_synthetic_sampled_slices():
     pats, offs, nsub = make_patterns(seed, n, 32, 64, 7)
     k = 4
     W = n - k
+    apm_b200.set_option("kernel", kernel)
     with apm_b200.Plan(pats, k) as plan:
         plan.count_device(dev.data_ptr(), 0, n, n, 0, W)
         whole = plan.read_counts()

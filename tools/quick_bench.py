@@ -22,8 +22,7 @@ def main():
     props = torch.cuda.get_device_properties(dev)
     print(json.dumps({"gpu": props.name, "sms": props.multi_processor_count}), flush=True)
     peaks = {}
-    for kind, name in ((0, "lop3+iadd3"), (1, "lop3"), (2, "add"), (3, "lop3+imad"), (4, "imad.wide"),
-                       (5, "lop3+imad.wide"), (6, "imad"), (7, "imad.hi"), (8, "shf"), (9, "7lop3:3imad")):
+    for kind, name in ((0, "lop3+iadd3"), (1, "lop3"), (3, "lop3+imad")):
         ops, sec = apm_b200.int_peak(kind)
         peaks[name] = ops
         print(json.dumps({"int_peak": name, "Tops": ops / 1e12, "sec": sec,
@@ -34,17 +33,18 @@ def main():
     torch.cuda.synchronize()
     st = torch.cuda.current_stream().cuda_stream
     combos = []
-    for var in ("0", "1", "2"):
-        combos.append((64, 4, 64, "4", "512", 8 << 20, var))
-        combos.append((64, 4, 64, "2", "512", 8 << 20, var))
-        combos.append((32, 2, 64, "4", "512", 16 << 20, var))
-        combos.append((200, 10, 16, "1", "512", 4 << 20, var))
-        combos.append((200, 10, 16, "2", "512", 4 << 20, var))
-        combos.append((50, 0, 64, "4", "512", 8 << 20, var))
-    for m, k, P, rb, tile, slab, var in combos:
+    for kern in ("sliced", "myers"):
+        combos.append((64, 4, 64, "4", "512", 32 << 20, "0", kern))
+        combos.append((64, 4, 128, "4", "512", 32 << 20, "0", kern))
+        combos.append((32, 2, 64, "4", "512", 32 << 20, "0", kern))
+        combos.append((50, 0, 64, "4", "512", 32 << 20, "0", kern))
+        combos.append((48, 3, 64, "4", "512", 32 << 20, "0", kern))
+        combos.append((24, 2, 64, "4", "512", 32 << 20, "0", kern))
+    for m, k, P, rb, tile, slab, var, kern in combos:
         apm_b200.set_option("rblock", rb)
         apm_b200.set_option("tile", tile)
         apm_b200.set_option("variant", var)
+        apm_b200.set_option("kernel", kern)
         pats, _, _ = make_patterns(TEXT_SEED, n, P, m, 7)
         with apm_b200.Plan(pats, k) as plan:
             def step(i):
@@ -64,7 +64,7 @@ def main():
             nw = (m + 31) // 32
             cells = slab * P * m * m
             ops = slab * P * m * nw * 10
-            print(json.dumps({"m": m, "k": k, "P": P, "rblock": rb, "tile": tile, "variant": var, "slab": slab, "ms": ms,
+            print(json.dumps({"m": m, "k": k, "P": P, "kernel": kern, "rblock": rb, "tile": tile, "variant": var, "slab": slab, "ms": ms,
                               "GCUPS": cells / ms / 1e6, "Tiops": ops / ms / 1e9,
                               "frac_of_lop3_iadd3_peak": ops / (ms * 1e-3) / peaks["lop3+iadd3"]}), flush=True)
 
