@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- the contract benchmark of the approximate-pattern-matching hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[4], the configuration the metric "GCUPS at 1/2/4/8 B200" is quoted on):
+synthetic ACGT text of 2^34 bytes (counter-based generator, materialised in HBM, database-sharded over
+the N ranks with a 63-byte halo), 4096 patterns of length 64, approx_factor 4.  Evaluating the whole
+16 GiB x 4096 job directly is 2.9e17 DP cells (about an hour on one B200), so a STEP is one pass of the
+hot path over one SLAB of the rank's shard: `slab` consecutive window starts x all 4096 patterns, every
+DP cell evaluated (mode "direct", no filter).  Successive steps take successive slabs, so the text
+touched is never L2-resident from a previous step.  GCUPS is size independent for this path; scaling is
+weak (every rank processes its own slab per step).
+
+JSON line (rank 0): metric GCUPS (+ text GB/s in roofline_hbm), value = cells of all ranks / max-over-
+ranks device time, e2e = the same through the C-ABI one-shot call with HOST buffers (pinned text in,
+counts out, H2D/D2H and plan construction inside the timed region), roofline against the measured
+integer-pipe peak, cpu_baseline = the reference's own levenshtein() (oracle/_ref) on the host cores.
+
+--impl reference times the reference's CPU implementation (oracle/_ref/libapm_ref.so: unmodified
+src/utils.c levenshtein() in the OpenMP work split of src/patterns_over_ranks.c:353-357) on a bounded
+sample of the same workload with all host threads.  The oracle is used here only as the thing measured
+for that arm / the cpu_baseline, and as the parity checker -- never inside the product path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG_DIR = os.path.join(ROOT, "inf560-approximate-pattern-matching_b200")
+for p in (ROOT, PKG_DIR):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+N_TOTAL = 1 << 34
+NB_PATTERNS = 4096
+M = 64
+K_ERR = 4
+SUBMOD = 7
+METRIC = "GCUPS"
+WORKLOAD = ("config5: synthetic 16 GiB ACGT text (2^34 B, DB-sharded with 63 B halo), 4096 patterns m=64, k=4; "
+            "step = one slab of the rank's shard x all patterns, every DP cell evaluated")
+
+
+def cells_full(windows: int, nb_patterns: int, m: int) -> float:
+    return float(windows) * nb_patterns * m * m
+
+
+def cells_text(n: int, nb_patterns: int, m: int, k: int) -> float:
+    """cells of a complete text of n bytes (full windows + truncated tail)."""
+    full = max(0, n - m + 1) * m * m
+    tail = sum(s * s for s in range(k + 1, m)) if n >= m else sum(s * s for s in range(k + 1, n + 1))
+    return float(nb_patterns) * (full + tail)
+
+
+def algorithmic_ops(windows: int, nb_patterns: int, m: int) -> float:
+    """10 * s * ceil(s/32) int32 ops per (pattern, window of size s)."""
+    return float(windows) * nb_patterns * 10 * m * ((m + 31) // 32)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.ok = index, [], set(), None, False
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            self.ok = True
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:  # NVML missing: report it, do not fail the bench
+            self.error = repr(e)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": getattr(self, "error", "no samples")}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own levenshtein() on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_rate(sample_bytes: int, nb_patterns: int, repeats: int = 1):
+    """-> (GCUPS, seconds, cores, kind, sample description).  Bounded sample of the same workload."""
+    from apm_b200.synth import TEXT_SEED, make_patterns, text_slice
+    from oracle import oracle
+    text = text_slice(TEXT_SEED, 0, sample_bytes).tobytes()
+    pats, _, _ = make_patterns(TEXT_SEED, N_TOTAL, NB_PATTERNS, M, SUBMOD)
+    pats = pats[:nb_patterns]
+    if oracle.have_ref():
+        kind, cores = "reference", int(oracle.ref().ref_max_threads())
+        fn = lambda: oracle.ref_count_matches(text, pats, K_ERR, mode=1, threads=cores)  # noqa: E731
+    else:
+        kind, cores = "port", oracle.max_threads()
+        fn = lambda: oracle.count_matches(text, pats, K_ERR, threads=cores)  # noqa: E731
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    cells = cells_text(sample_bytes, nb_patterns, M, K_ERR)
+    sample = (f"first {sample_bytes} B of the config-5 text x first {nb_patterns} patterns (m=64, k=4), "
+              f"{cells:.3g} cells, OpenMP position split of patterns_over_ranks.c:353-357")
+    return cells / best / 1e9, best, cores, kind, sample
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_bytes, npat = 96 * 1024, 16
+    times = []
+    gc = cores = kind = sample = None
+    for i in range(args.warmup + args.steps):
+        gc, dt, cores, kind, sample = cpu_reference_rate(sample_bytes, npat)
+        if i >= args.warmup:
+            times.append(dt)
+    mean_t = sum(times) / len(times)
+    value = cells_text(sample_bytes, npat, M, K_ERR) / mean_t / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": mean_t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "step": sample, "threads": cores},
+        "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import apm_b200
+    from apm_b200.synth import TEXT_SEED, make_patterns
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    apm_b200.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    apm_b200.set_option("kernel", args.kernel)
+    apm_b200.set_option("gpus", "1")
+
+    # ---- this rank's database shard: window starts [j0, j1), bytes [j0, j1 + M - 1) --------------
+    W = N_TOTAL - K_ERR
+    j0 = (W * rank // world) & ~15
+    j1 = W if rank == world - 1 else (W * (rank + 1) // world) & ~15
+    b0, b1 = j0, min(N_TOTAL, j1 + M - 1)
+    shard = torch.empty(b1 - b0, dtype=torch.uint8, device=dev)
+    apm_b200.synth_text_device(shard.data_ptr(), TEXT_SEED, b0, b1 - b0)
+    torch.cuda.synchronize()
+
+    pats, offs, nsub = make_patterns(TEXT_SEED, N_TOTAL, NB_PATTERNS, M, SUBMOD)
+    plan = apm_b200.Plan(pats, K_ERR)
+    slab = args.slab_windows
+    nslabs = max(1, (j1 - j0 - 2 * M) // slab)
+    stream = torch.cuda.current_stream().cuda_stream
+    counts_ptr = plan.counts_device_ptr()
+    reduced = torch.zeros(NB_PATTERNS, dtype=torch.int64, device=dev) if world > 1 else None
+
+    def step(i: int) -> None:
+        a = j0 + (i % nslabs) * slab
+        plan.count_device(shard.data_ptr(), b0, b1 - b0, N_TOTAL, a, a + slab, stream)
+        if world > 1:
+            # the only exchange of the path: the per-pattern count vector (32 KB) summed over NCCL/NVLink.
+            # A copy is reduced so that the plan's accumulating counters stay per-rank partial sums.
+            reduced.copy_(_tensor_from_ptr(torch, counts_ptr, NB_PATTERNS, dev))
+            dist.all_reduce(reduced, op=dist.ReduceOp.SUM)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    for i in range(args.warmup):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = apm_b200.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    sync_all()
+    clocks = sampler.stop()
+    launches = apm_b200.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    ms_step = ms_total / args.steps
+    cells_step = cells_full(slab, NB_PATTERNS, M) * world
+    value = cells_step / (ms_step * 1e-3) / 1e9
+
+    # ---- end-to-end through the one-shot C-ABI call with HOST buffers ------------------------------
+    e2e_windows = args.e2e_windows
+    host_text = torch.empty(e2e_windows + M - 1, dtype=torch.uint8).pin_memory()
+    host_text.copy_(shard[: e2e_windows + M - 1])
+    torch.cuda.synchronize()
+    e2e_times = []
+    for i in range(2 + args.e2e_steps):
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        got = apm_b200.count_matches_ptr(host_text.data_ptr(), host_text.numel(), pats, K_ERR)
+        dt = time.perf_counter() - t0
+        if i >= 2:
+            e2e_times.append(dt)
+    e2e_dt = sum(e2e_times) / len(e2e_times)
+    if world > 1:
+        t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_cells = cells_text(host_text.numel(), NB_PATTERNS, M, K_ERR) * world
+    e2e = {"value": e2e_cells / e2e_dt / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(host_text.numel() + NB_PATTERNS * M),
+           "d2h_bytes_per_step": 8 * NB_PATTERNS, "ms_per_step": e2e_dt * 1e3,
+           "call": "apm_count_matches(host text slab + halo, 4096 patterns, k=4): plan build + H2D + kernels + D2H"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline: measured integer-pipe peak, algorithmic ops of SURVEY.md section 8d --------------
+    peak0, _ = apm_b200.int_peak(0)  # LOP3 + IADD3 (ptxas turns the add into IMAD.IADD: both pipes)
+    peak3, _ = apm_b200.int_peak(3)  # LOP3 + IMAD
+    peak1, _ = apm_b200.int_peak(1)  # LOP3 only: the ALU pipe every boolean instruction has to use
+    int_peak = max(peak0, peak3)
+    alg_ops = algorithmic_ops(slab, NB_PATTERNS, M)
+    achieved = alg_ops / (ms_step * 1e-3)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    text_gbs = slab * world / (ms_step * 1e-3) / 1e9
+    roofline = {
+        "bound": "int_alu", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tiop/s",
+        "frac": achieved / int_peak, "traffic": None,
+        "kernel": "sliced_count_kernel<64>" if args.kernel in ("auto", "sliced") else "myers_count_kernel<2,4,0>",
+        "algorithmic_ops_per_unit": "10*m*ceil(m/32) = 1280 int32 ops per (pattern, window), SURVEY.md 8d",
+        "peak_source": "measured in this run: max(LOP3+IADD3, LOP3+IMAD) dependency-free microbenchmark",
+        "lop3_only_peak": peak1 / 1e12,
+        "note": "the boolean work can only issue on the ALU pipe (LOP3-only peak); the sliced kernel executes "
+                "5*m*m/32 = 640 LOP3 per unit, the row-parallel Myers kernel ~1170 ALU-pipe instructions",
+    }
+    roofline_hbm = {"bound": "hbm", "achieved": text_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": text_gbs / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                    "note": "text bytes per second; the path is compute bound by construction (>1e5 int ops per text byte)"}
+
+    # ---- parity spot check of the timed path against the oracle -------------------------------------
+    parity = "skipped"
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import oracle
+        L = 12288
+        a = j0 + slab // 2
+        sel = [0, 1, 2, 3, 4, 5, 6, 3500]
+        sub = apm_b200.Plan([pats[i] for i in sel], K_ERR)
+        sub.count_device(shard.data_ptr(), b0, b1 - b0, N_TOTAL, a, a + L, stream)
+        got = sub.read_counts(stream)
+        seg = oracle.synth_text(TEXT_SEED, a, L + M - 1).tobytes() + b"\0" * M
+        want = [oracle.count_range(seg, pats[i], K_ERR, 0, L) for i in sel]
+        sub.close()
+        parity = "ok" if got == want else f"MISMATCH got={got} want={want}"
+        gc, dt, cores, kind, sample = cpu_reference_rate(160 * 1024, 16)
+        cpu = {"value": gc, "unit": "GCUPS", "cores": cores, "kind": kind, "sample": sample, "seconds": dt}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "slab_windows": slab, "patterns": NB_PATTERNS, "m": M, "k": K_ERR,
+                   "kernel": args.kernel, "mode": "direct", "shard": "db", "l2": "successive steps read successive "
+                   "slabs of a 16 GiB text (inputs larger than L2)", "text_bytes_per_rank": int(b1 - b0)},
+        "text_gbs": text_gbs, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "parity": parity,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _tensor_from_ptr(torch, ptr: int, n: int, dev):
+    """int64 tensor aliasing n device words at `ptr` (CUDA array interface)."""
+
+    class _Holder:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+    return torch.as_tensor(_Holder(), device=dev)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--kernel", choices=["auto", "sliced", "myers"], default="auto")
+    ap.add_argument("--slab-windows", type=int, default=1 << 20, help="window starts per step and rank")
+    ap.add_argument("--e2e-windows", type=int, default=1 << 20)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip cpu_baseline + parity spot check")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

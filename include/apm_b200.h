@@ -74,6 +74,10 @@ const char *apm_get_option(const char *key);
 
 const char *apm_last_error(void);
 int apm_device_count(int *count);
+/* Makes `device` current for the calling thread inside the library's CUDA runtime (replaces setDevice,
+ * src/cuda_utils.cu:22-35).  The one-shot API uses the current device, plus the following ones when
+ * "gpus" > 1; apm_plan_create binds the plan to the current device.                                */
+int apm_set_device(int device);
 
 /* ---- planned / device-resident API (stream-ordered, no host synchronisation) ------------------- */
 

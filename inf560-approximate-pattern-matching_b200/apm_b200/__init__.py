@@ -24,7 +24,7 @@ APM_OK, APM_EINVAL, APM_ENODEVICE, APM_ECUDA, APM_EIO, APM_ENOMEM = range(6)
 # every symbol include/apm_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "apm_count_matches", "apm_count_matches_file", "apm_set_option", "apm_get_option", "apm_last_error",
-    "apm_device_count", "apm_plan_create", "apm_plan_destroy", "apm_plan_count_device",
+    "apm_device_count", "apm_set_device", "apm_plan_create", "apm_plan_destroy", "apm_plan_count_device",
     "apm_plan_set_pattern_shard", "apm_plan_zero_counts", "apm_plan_counts_device_ptr",
     "apm_plan_read_counts", "apm_plan_max_pattern_len", "apm_synth_text_device", "apm_int_peak",
     "apm_launch_count", "apm_version",
@@ -57,6 +57,7 @@ def lib():
     L.apm_get_option.restype = C.c_char_p
     L.apm_last_error.restype = C.c_char_p
     L.apm_device_count.argtypes = [vp]
+    L.apm_set_device.argtypes = [C.c_int]
     L.apm_plan_create.argtypes = [vp, vp, C.c_int, C.c_int, vp]
     L.apm_plan_destroy.argtypes = [vp]
     L.apm_plan_count_device.argtypes = [vp, vp, ull, ull, ull, ull, ull, vp]
@@ -100,6 +101,10 @@ def device_count() -> int:
     n = C.c_int(0)
     _check(lib().apm_device_count(C.byref(n)))
     return n.value
+
+
+def set_device(device: int) -> None:
+    _check(lib().apm_set_device(device))
 
 
 def launch_count() -> int:

@@ -323,17 +323,10 @@ int launch_myers(apm_plan *pl, Bucket &b, const uint8_t *d_buf, long long buf_le
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, b.fn, kThreads, smem));
     if (occ < 1) return fail(APM_ECUDA, "myers kernel NW=%d R=%d does not fit an SM (smem %zu)", b.NW, b.R, smem);
     const long long capacity = (long long)pl->num_sms * occ;
-    unsigned gx, gy = 1;
-    if (ntiles >= capacity) {
-        gx = (unsigned)capacity;
-    } else {
-        gx = (unsigned)ntiles;
-        long long want_y = std::min<long long>(b.ngroups, (capacity + ntiles - 1) / ntiles);
-        gpc = std::min(gpc, (int)((b.ngroups + want_y - 1) / want_y));
-        const int nchunks = (b.ngroups + gpc - 1) / gpc;
-        gy = (unsigned)std::min<long long>(want_y, nchunks);
-        smem = myers_smem_bytes(tile, b.mmax, gpc, pl->ncodes, b.R, b.NW);
-    }
+    // shrink the chunk until every resident CTA gets >= ~8 (chunk, tile) items
+    gpc = (int)std::max<long long>(1, std::min<long long>(gpc, ntiles * b.ngroups / (8 * capacity)));
+    const long long nitems = ntiles * ((b.ngroups + gpc - 1) / gpc);
+    const unsigned gx = (unsigned)std::min<long long>(nitems, capacity), gy = 1;
 
     MyersArgs a;
     a.buf = d_buf;
@@ -364,6 +357,7 @@ template <int MC>
 int launch_sliced_mc(apm_plan *pl, SlicedList &l, const SlicedArgs &base, long long nwin, cudaStream_t st) {
     auto fn = sliced_count_kernel<MC>;
     const long long ntiles = (nwin + kSlicedTile - 1) / kSlicedTile;
+    // occupancy with the largest chunk, then shrink the chunk until every resident CTA gets >= ~8 items
     int ppc = std::min(l.npat, 128);
     size_t smem = sliced_smem_bytes<MC>(ppc, pl->nplanes);
     if (smem > l.smem_set) {
@@ -374,17 +368,11 @@ int launch_sliced_mc(apm_plan *pl, SlicedList &l, const SlicedArgs &base, long l
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kSlicedThreads, smem));
     if (occ < 1) return fail(APM_ECUDA, "sliced kernel MC=%d does not fit an SM (smem %zu)", MC, smem);
     const long long capacity = (long long)pl->num_sms * occ;
-    unsigned gx, gy = 1;
-    if (ntiles >= capacity) {
-        gx = (unsigned)capacity;
-    } else {
-        gx = (unsigned)ntiles;
-        const long long want_y = std::min<long long>(l.npat, (capacity + ntiles - 1) / ntiles);
-        ppc = std::min(ppc, (int)((l.npat + want_y - 1) / want_y));
-        const int nchunks = (l.npat + ppc - 1) / ppc;
-        gy = (unsigned)std::min<long long>(want_y, nchunks);
-        smem = sliced_smem_bytes<MC>(ppc, pl->nplanes);
-    }
+    const long long pattern_tiles = ntiles * l.npat;
+    ppc = (int)std::max<long long>(1, std::min<long long>(ppc, pattern_tiles / (8 * capacity)));
+    const long long nitems = ntiles * ((l.npat + ppc - 1) / ppc);
+    const unsigned gx = (unsigned)std::min<long long>(nitems, capacity);
+    const unsigned gy = 1;
     SlicedArgs a = base;
     a.pats_per_chunk = ppc;
     fn<<<dim3(gx, gy), kSlicedThreads, smem, st>>>(a);
@@ -511,6 +499,15 @@ int apm_device_count(int *count) {
     int rc = device_ready(&n);
     *count = rc ? 0 : n;
     return rc;
+}
+
+int apm_set_device(int device) {
+    int n = 0;
+    int rc = device_ready(&n);
+    if (rc) return rc;
+    if (device < 0 || device >= n) return fail(APM_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    CUDA_TRY(cudaSetDevice(device));
+    return APM_OK;
 }
 
 int apm_set_option(const char *key, const char *value) {
@@ -904,8 +901,8 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
     };
     for (int g = 0; g < G; ++g) {
         DevJob &j = jobs[g];
-        j.dev = g;
-        if (cudaSetDevice(g) != cudaSuccess) return bail(fail(APM_ECUDA, "cudaSetDevice(%d) failed", g));
+        j.dev = (restore + g) % ndev;  // the current device first
+        if (cudaSetDevice(j.dev) != cudaSuccess) return bail(fail(APM_ECUDA, "cudaSetDevice(%d) failed", j.dev));
         if (cudaStreamCreateWithFlags(&j.st, cudaStreamNonBlocking) != cudaSuccess)
             return bail(fail(APM_ECUDA, "cudaStreamCreate failed on device %d", g));
         if ((rc = apm_plan_create(patterns, pattern_len, nb_patterns, approx_factor, &j.plan))) return bail(rc);

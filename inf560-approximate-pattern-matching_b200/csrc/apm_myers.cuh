@@ -22,6 +22,7 @@
 //               global atomic per (CTA, pattern, chunk)
 #pragma once
 #include "apm_common.cuh"
+#include "apm_tile.cuh"
 
 namespace apm {
 
@@ -242,10 +243,7 @@ struct MyersArgs {
 };
 
 // Shared-memory layout (dynamic): see myers_smem_bytes() -- the host uses the same formula.
-__host__ __device__ inline size_t myers_tile_cap(int tile, int mmax) {
-    // tile + halo, + up to 15 bytes of leading misalignment, rounded up to 16, + one spare 16-byte row
-    return (size_t)((tile + mmax - 1 + 15 + 15) / 16) * 16 + 16;
-}
+__host__ __device__ inline size_t myers_tile_cap(int tile, int mmax) { return tile_cap(tile, mmax - 1); }
 __host__ __device__ inline size_t myers_smem_bytes(int tile, int mmax, int groups_per_chunk, int ncodes,
                                                    int R, int NW) {
     const size_t cap = myers_tile_cap(tile, mmax);
@@ -339,87 +337,55 @@ __global__ void __launch_bounds__(kThreads) myers_count_kernel(const MyersArgs a
 
     const long long nwin = a.w1 - a.w0;
     const long long ntiles = (nwin + a.tile - 1) / a.tile;
-    const uintptr_t gbase = reinterpret_cast<uintptr_t>(a.buf);
     const int slots = a.tile / kThreads;
     uint32_t phase = 0;  // bit s = parity to wait for on barrier s
 
-    // Geometry of a tile: local byte range [ts, te) needed, a0 = 16-byte aligned origin of the
-    // shared buffers (smem index of local byte i is i - a0), [ta, tb) = part fetched by TMA.
-    auto geometry = [&](long long t, long long &ts, long long &te, long long &a0, long long &ta, long long &tb) {
-        ts = a.w0 + t * a.tile;
-        te = ts + a.tile + a.mmax - 1;
-        if (te > a.buf_len) te = a.buf_len;
-        a0 = ts - (long long)((gbase + (uintptr_t)ts) & 15);
-        ta = a0 < 0 ? a0 + 16 : a0;
-        tb = a0 + ((te - a0 + 15) / 16) * 16;
-        if (tb > a.buf_len) tb -= 16;
-    };
-    auto issue = [&](long long t, int stage) {  // one thread
-        long long ts, te, a0, ta, tb;
-        geometry(t, ts, te, a0, ta, tb);
-        if (tb > ta) {
-            const uint32_t bytes = (uint32_t)(tb - ta);
-            mbar_arrive_expect_tx(&bars[stage], bytes);
-            tma_bulk_g2s(s_raw0 + stage * cap + (ta - a0), a.buf + ta, bytes, &bars[stage]);
-        }
-    };
-
+    // Work items = (pattern chunk, text tile), chunk-major, dealt round-robin to the persistent CTAs; the
+    // text tile of the CTA's next item is prefetched by TMA while the current one is being processed.
+    const int halo = a.mmax - 1;
     const int nchunks = (a.ngroups + a.groups_per_chunk - 1) / a.groups_per_chunk;
-    for (int chunk = blockIdx.y; chunk < nchunks; chunk += gridDim.y) {
-        const int g0 = chunk * a.groups_per_chunk;
-        const int gcount = min(a.groups_per_chunk, a.ngroups - g0);
-        // ---- stage this chunk's Peq tables, lengths, pattern ids; zero the CTA-local counters
-        {
-            const uint32_t *src = a.peq + (size_t)g0 * a.ncodes * EW;
-            const int nw = gcount * a.ncodes * EW;
-            for (int i = tid; i < nw; i += kThreads) s_peq[i] = src[i];
-            for (int i = tid; i < gcount; i += kThreads) s_gm[i] = a.group_m[g0 + i];
-            for (int i = tid; i < gcount * R; i += kThreads) {
-                s_gpat[i] = a.group_pat[(size_t)g0 * R + i];
-                s_cnt[i] = 0;
+    const long long nitems = ntiles * nchunks;
+    int cur_chunk = -1, gcount = 0, stage = 0;
+    long long it = blockIdx.x;
+    if (tid == 0 && it < nitems)
+        tile_issue(tile_geometry(a.buf, a.buf_len, a.w0, it % ntiles, a.tile, halo), a.buf, s_raw0, &bars[0]);
+    {
+        for (; it < nitems; it += gridDim.x) {
+            const long long itn = it + gridDim.x;
+            if (tid == 0 && itn < nitems)  // prefetch the next item's tile
+                tile_issue(tile_geometry(a.buf, a.buf_len, a.w0, itn % ntiles, a.tile, halo), a.buf,
+                           s_raw0 + (stage ^ 1) * cap, &bars[stage ^ 1]);
+            const int chunk = (int)(it / ntiles);
+            const long long t = it % ntiles;
+            if (chunk != cur_chunk) {
+                // flush the CTA-local counters of the previous chunk, then stage this chunk's Peq tables,
+                // lengths and pattern ids (thread i owns slot i in both loops)
+                for (int i = tid; i < gcount * R; i += kThreads) {
+                    const int p = s_gpat[i];
+                    const uint32_t c = s_cnt[i];
+                    if (p >= 0 && c) atomicAdd(&a.counts[p], (unsigned long long)c);
+                }
+                const int g0 = chunk * a.groups_per_chunk;
+                gcount = min(a.groups_per_chunk, a.ngroups - g0);
+                for (int i = tid; i < gcount * R; i += kThreads) {
+                    s_gpat[i] = a.group_pat[(size_t)g0 * R + i];
+                    s_cnt[i] = 0;
+                }
+                const uint32_t *src = a.peq + (size_t)g0 * a.ncodes * EW;
+                const int nw = gcount * a.ncodes * EW;
+                for (int i = tid; i < nw; i += kThreads) s_peq[i] = src[i];
+                for (int i = tid; i < gcount; i += kThreads) s_gm[i] = a.group_m[g0 + i];
+                cur_chunk = chunk;
             }
-        }
-        int stage = 0;
-        long long t = blockIdx.x;
-        if (tid == 0 && t < ntiles) issue(t, 0);
-        __syncthreads();
-
-        for (; t < ntiles; t += gridDim.x) {
-            const long long tn = t + gridDim.x;
-            if (tid == 0 && tn < ntiles) issue(tn, stage ^ 1);  // prefetch the next tile
-
-            long long ts, te, a0, ta, tb;
-            geometry(t, ts, te, a0, ta, tb);
-            if (tb > ta) {
+            const TileGeom tg = tile_geometry(a.buf, a.buf_len, a.w0, t, a.tile, halo);
+            const long long ts = tg.ts, a0 = tg.a0;
+            if (tg.tb > tg.ta) {
                 mbar_wait(&bars[stage], (phase >> stage) & 1u);
                 phase ^= (1u << stage);
             }
-            // ---- raw bytes -> compact alphabet codes (fringe bytes outside the TMA box come
-            //      straight from global memory)
-            {
-                const uint8_t *raw = s_raw0 + stage * cap;
-                const int nwords = (int)((te - a0 + 3) / 4);
-                for (int q = tid; q < nwords; q += kThreads) {
-                    const long long i0 = a0 + 4ll * q;
-                    uint32_t out;
-                    if (i0 >= ta && i0 + 4 <= tb) {
-                        const uint32_t w = reinterpret_cast<const uint32_t *>(raw)[q];
-                        out = (uint32_t)s_map[w & 0xFF] | ((uint32_t)s_map[(w >> 8) & 0xFF] << 8) |
-                              ((uint32_t)s_map[(w >> 16) & 0xFF] << 16) | ((uint32_t)s_map[w >> 24] << 24);
-                    } else {
-                        out = 0;
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const long long i = i0 + b;
-                            uint32_t byte = 0;
-                            if (i >= ta && i < tb) byte = raw[4 * q + b];
-                            else if (i >= 0 && i < a.buf_len) byte = a.buf[i];
-                            out |= (uint32_t)s_map[byte] << (8 * b);
-                        }
-                    }
-                    reinterpret_cast<uint32_t *>(s_codes)[q] = out;
-                }
-            }
+            // raw bytes -> compact alphabet codes (fringe bytes outside the TMA box come from global memory)
+            tile_encode(tg, a.buf, a.buf_len, s_raw0 + stage * cap, s_map, s_map[0], s_codes,
+                        (int)((tg.te - tg.a0 + 3) / 4 * 4), tid, kThreads);
             __syncthreads();
 
             // ---- the hot loop: groups (R patterns) x window slots x m columns
@@ -469,13 +435,11 @@ __global__ void __launch_bounds__(kThreads) myers_count_kernel(const MyersArgs a
             __syncthreads();  // codes + raw[stage] free for reuse
             stage ^= 1;
         }
-        // ---- flush the CTA-local counters of this chunk
-        for (int i = tid; i < gcount * R; i += kThreads) {
-            const int p = s_gpat[i];
-            const uint32_t c = s_cnt[i];
-            if (p >= 0 && c) atomicAdd(&a.counts[p], (unsigned long long)c);
-        }
-        __syncthreads();
+    }
+    for (int i = tid; i < gcount * R; i += kThreads) {
+        const int p = s_gpat[i];
+        const uint32_t c = s_cnt[i];
+        if (p >= 0 && c) atomicAdd(&a.counts[p], (unsigned long long)c);
     }
 }
 

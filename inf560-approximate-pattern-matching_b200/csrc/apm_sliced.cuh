@@ -162,27 +162,37 @@ __global__ void __launch_bounds__(kSlicedThreads) sliced_count_kernel(const Slic
     constexpr int span = sliced_span(MC);  // bytes re-coded per tile (<= cap)
     uint32_t phase = 0;
 
+    // Work items = (pattern chunk, text tile), chunk-major, dealt round-robin to the persistent CTAs; the
+    // text tile of the CTA's next item is prefetched by TMA while the current one is being processed.
     const int nchunks = (a.npat + a.pats_per_chunk - 1) / a.pats_per_chunk;
-    for (int chunk = blockIdx.y; chunk < nchunks; chunk += gridDim.y) {
-        const int p0 = chunk * a.pats_per_chunk;
-        const int pcount = min(a.pats_per_chunk, a.npat - p0);
-        for (int i = tid; i < pcount * MC; i += kSlicedThreads) s_pc[i] = a.pat_codes[(size_t)p0 * MC + i];
-        for (int i = tid; i < pcount; i += kSlicedThreads) {
-            s_pm[i] = a.pat_m[p0 + i];
-            s_pid[i] = a.pat_id[p0 + i];
-            s_cnt[i] = 0;
-        }
-        int stage = 0;
-        long long t = blockIdx.x;
-        if (tid == 0 && t < ntiles)
-            tile_issue(tile_geometry(a.buf, a.buf_len, a.w0, t, kSlicedTile, MC), a.buf, s_raw0, &bars[0]);
-        __syncthreads();
-
-        for (; t < ntiles; t += gridDim.x) {
-            const long long tn = t + gridDim.x;
-            if (tid == 0 && tn < ntiles)
-                tile_issue(tile_geometry(a.buf, a.buf_len, a.w0, tn, kSlicedTile, MC), a.buf,
+    const long long nitems = ntiles * nchunks;
+    int cur_chunk = -1, pcount = 0, stage = 0;
+    long long it = blockIdx.x;
+    if (tid == 0 && it < nitems)
+        tile_issue(tile_geometry(a.buf, a.buf_len, a.w0, it % ntiles, kSlicedTile, MC), a.buf, s_raw0, &bars[0]);
+    {
+        for (; it < nitems; it += gridDim.x) {
+            const long long itn = it + gridDim.x;
+            if (tid == 0 && itn < nitems)
+                tile_issue(tile_geometry(a.buf, a.buf_len, a.w0, itn % ntiles, kSlicedTile, MC), a.buf,
                            s_raw0 + (stage ^ 1) * cap, &bars[stage ^ 1]);
+            const int chunk = (int)(it / ntiles);
+            const long long t = it % ntiles;
+            if (chunk != cur_chunk) {  // (re)load the chunk's patterns; thread i owns slot i of both loops
+                const int p0 = chunk * a.pats_per_chunk;
+                for (int i = tid; i < pcount; i += kSlicedThreads) {
+                    const uint32_t c = s_cnt[i];
+                    if (c) atomicAdd(&a.counts[s_pid[i]], (unsigned long long)c);
+                }
+                pcount = min(a.pats_per_chunk, a.npat - p0);
+                for (int i = tid; i < pcount; i += kSlicedThreads) {
+                    s_pm[i] = a.pat_m[p0 + i];
+                    s_pid[i] = a.pat_id[p0 + i];
+                    s_cnt[i] = 0;
+                }
+                for (int i = tid; i < pcount * MC; i += kSlicedThreads) s_pc[i] = a.pat_codes[(size_t)p0 * MC + i];
+                cur_chunk = chunk;
+            }
             const TileGeom g = tile_geometry(a.buf, a.buf_len, a.w0, t, kSlicedTile, MC);
             if (g.tb > g.ta) {
                 mbar_wait(&bars[stage], (phase >> stage) & 1u);
@@ -286,11 +296,10 @@ __global__ void __launch_bounds__(kSlicedThreads) sliced_count_kernel(const Slic
             __syncthreads();  // U, codes, raw[stage] free for reuse
             stage ^= 1;
         }
-        for (int i = tid; i < pcount; i += kSlicedThreads) {
-            const uint32_t c = s_cnt[i];
-            if (c) atomicAdd(&a.counts[s_pid[i]], (unsigned long long)c);
-        }
-        __syncthreads();
+    }
+    for (int i = tid; i < pcount; i += kSlicedThreads) {
+        const uint32_t c = s_cnt[i];
+        if (c) atomicAdd(&a.counts[s_pid[i]], (unsigned long long)c);
     }
 }
 
