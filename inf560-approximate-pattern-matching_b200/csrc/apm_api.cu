@@ -357,8 +357,21 @@ template <int MC>
 int launch_sliced_mc(apm_plan *pl, SlicedList &l, const SlicedArgs &base, long long nwin, cudaStream_t st) {
     auto fn = sliced_count_kernel<MC>;
     const long long ntiles = (nwin + kSlicedTile - 1) / kSlicedTile;
-    // occupancy with the largest chunk, then shrink the chunk until every resident CTA gets >= ~8 items
-    int ppc = std::min(l.npat, 128);
+    // chunk size: as large as still allows the best occupancy the U table permits (3 CTAs/SM for the DNA
+    // alphabet), then shrunk until every resident CTA gets >= ~8 (chunk, tile) items
+    int dev_smem_sm = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&dev_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, pl->device));
+    const int max_ctas = MC == 64 ? 3 : 4;
+    int ppc = 1;
+    for (int ctas = max_ctas; ctas >= 1; --ctas) {
+        const long long budget = (long long)dev_smem_sm / ctas - 1024;  // 1 KB per CTA is reserved by the system
+        const long long room = budget - (long long)sliced_smem_bytes<MC>(0, pl->nplanes);
+        if (room >= (long long)8 * (MC + 12)) {
+            ppc = (int)std::min<long long>(128, room / (MC + 12));
+            break;
+        }
+    }
+    ppc = std::min(ppc, l.npat);
     size_t smem = sliced_smem_bytes<MC>(ppc, pl->nplanes);
     if (smem > l.smem_set) {
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
