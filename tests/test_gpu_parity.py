@@ -330,3 +330,69 @@ def test_large_synthetic_sampled_slices(kernel):
                 else:  # interior slice: pad so the oracle does not truncate at the slice end
                     want = oracle.count_range(seg + b"\0" * 64, pats[p], k, 0, L)
                 assert got[p] == want, (a, p)
+
+
+# ---------------------------------------------------------------------------------------------
+# one-process-per-GPU host layer (apm_b200/dist.py) with the CUDA counter
+# ---------------------------------------------------------------------------------------------
+def test_dist_layer_cuda_counter_single_rank():
+    from apm_b200 import dist as adist
+    text = oracle.synth_text(0x5EED0001, 4242, 50_000)
+    pats = [text[100:164].tobytes(), text[30000:30050].tobytes(), text[-25:].tobytes() + b"ACGT", b"ACGTACGTAC"]
+    k = 2
+    want = oracle.count_matches(text.tobytes(), pats, k)
+    got = adist.count_matches_distributed(lambda off, cnt: text[off:off + cnt], len(text), pats, k)
+    assert got == want
+    # emulate 3 DB shards / 3 pattern shards in one process: partial sums add up to the whole
+    m_max = max(len(p) for p in pats)
+    total = [0] * len(pats)
+    for r in range(3):
+        j0, j1, b0, b1 = adist.db_shard(len(text), k, m_max, r, 3)
+        part = adist.cuda_counter(text[b0:b1], b0, len(text), j0, j1, pats, k)
+        total = [a + b for a, b in zip(total, part)]
+    assert total == want
+    total = [0] * len(pats)
+    for r in range(3):
+        part = adist.cuda_counter(text, 0, len(text), 0, len(text) - k, pats, k, pattern_shard=(r, 3))
+        total = [a + b for a, b in zip(total, part)]
+    assert total == want
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from apm_b200 import dist as adist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    text = oracle.synth_text(0x5EED0001, 99, 300_000)
+    pats = [text[1000:1064].tobytes(), text[150000:150064].tobytes(), text[-30:].tobytes() + b"ACGTAC"]
+    out = {}
+    for shard in ("db", "patterns"):
+        out[shard] = adist.count_matches_distributed(lambda off, cnt: text[off:off + cnt], len(text), pats, 3,
+                                                     shard=shard, device=torch.device("cuda", rank))
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_dist_layer_nccl_two_gpus():
+    torch = _torch()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    text = oracle.synth_text(0x5EED0001, 99, 300_000)
+    pats = [text[1000:1064].tobytes(), text[150000:150064].tobytes(), text[-30:].tobytes() + b"ACGTAC"]
+    apm_b200.set_option("kernel", "dp")
+    want = apm_b200.count_matches(text.tobytes(), pats, 3)
+    for rank, out in res:
+        assert out["db"] == want and out["patterns"] == want
