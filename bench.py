@@ -118,11 +118,12 @@ def cpu_reference_rate(sample_bytes: int, nb_patterns: int, repeats: int = 1):
     text = text_slice(TEXT_SEED, 0, sample_bytes).tobytes()
     pats, _, _ = make_patterns(TEXT_SEED, N_TOTAL, NB_PATTERNS, M, SUBMOD)
     pats = pats[:nb_patterns]
-    if oracle.have_ref():
-        kind, cores = "reference", int(oracle.ref().ref_max_threads())
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if oracle.have_ref():  # all host threads, whatever OMP_NUM_THREADS torchrun exported
+        kind, cores = "reference", ncpu
         fn = lambda: oracle.ref_count_matches(text, pats, K_ERR, mode=1, threads=cores)  # noqa: E731
     else:
-        kind, cores = "port", oracle.max_threads()
+        kind, cores = "port", ncpu
         fn = lambda: oracle.count_matches(text, pats, K_ERR, threads=cores)  # noqa: E731
     best = None
     for _ in range(repeats):
@@ -181,6 +182,7 @@ def run_ours(args) -> None:
     apm_b200.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     apm_b200.set_option("kernel", args.kernel)
     apm_b200.set_option("gpus", "1")
