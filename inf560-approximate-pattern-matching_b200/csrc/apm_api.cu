@@ -126,13 +126,16 @@ struct Bucket {
     int occ_cache_smem = -1, occ_cache = 0;
 };
 
-// patterns handled by the window-sliced kernel, one list per register-array size MC
+// patterns handled by the window-sliced kernel: one list for m <= 32 (MC = 32) and one for longer ones
 struct SlicedList {
-    int MC = 64, npat = 0, mmin = 0, mmax = 0;
-    std::vector<uint8_t> codes;  // [npat][MC]
+    int MC = 64, npat = 0, mmin = 0, mmax = 0, mcp = 0;
+    std::vector<uint8_t> codes;  // [npat][mcp]
     std::vector<int> m, id;
     uint8_t *d_codes = nullptr;
     int *d_m = nullptr, *d_id = nullptr;
+    uint2 *d_vscratch = nullptr;  // boundary deltas between column blocks (only when mmax > MC)
+    unsigned long long *d_work = nullptr;  // item dispenser of the persistent kernel
+    size_t vscratch_bytes = 0;
     size_t smem_set = 0;
 };
 
@@ -180,6 +183,8 @@ void free_work(apm_plan *pl) {
         cudaFree(l.d_codes);
         cudaFree(l.d_m);
         cudaFree(l.d_id);
+        cudaFree(l.d_vscratch);
+        cudaFree(l.d_work);
     }
     pl->sliced.clear();
     cudaFree(pl->d_tail_list);
@@ -200,13 +205,13 @@ int build_work(apm_plan *pl) {
     for (int p = 0; p < pl->P; ++p) {
         if (p % pl->shard_world != pl->shard_rank) continue;
         const int m = (int)pl->pats[p].size();
-        if (pl->opt.kernel == KERNEL_DP || m > kMaxMyersLen) {
+        const bool sliced_ok = m <= kSlicedMaxLen && pl->nplanes <= kSlicedMaxPlanes &&
+                               (pl->opt.kernel == KERNEL_SLICED || pl->opt.kernel == KERNEL_AUTO);
+        if (pl->opt.kernel == KERNEL_DP || (m > kMaxMyersLen && !sliced_ok)) {
             pl->all_list.push_back(p);
             pl->all_mmax = std::max(pl->all_mmax, m);
             continue;
         }
-        const bool sliced_ok = m <= 64 && pl->nplanes <= kSlicedMaxPlanes &&
-                               (pl->opt.kernel == KERNEL_SLICED || pl->opt.kernel == KERNEL_AUTO);
         if (sliced_ok) sliced_ids[m <= 32 ? 0 : 1].push_back(p);
         else by_nw[(m + 31) / 32].push_back(p);
         const int tw = m - 1 - pl->k;  // number of truncated tail windows (sequential.c:121,131-134)
@@ -265,10 +270,11 @@ int build_work(apm_plan *pl) {
         l.npat = (int)ids.size();
         l.mmin = (int)pl->pats[ids.front()].size();
         l.mmax = (int)pl->pats[ids.back()].size();
-        l.codes.assign((size_t)l.npat * l.MC, 0);
+        l.mcp = (l.mmax + 2 + 15) / 16 * 16;  // the sweep reads two symbols ahead
+        l.codes.assign((size_t)l.npat * l.mcp + 16, 0);
         for (int i = 0; i < l.npat; ++i) {
             const std::string &s = pl->pats[ids[i]];
-            for (size_t x = 0; x < s.size(); ++x) l.codes[(size_t)i * l.MC + x] = pl->code_of[(uint8_t)s[x]];
+            for (size_t x = 0; x < s.size(); ++x) l.codes[(size_t)i * l.mcp + x] = pl->code_of[(uint8_t)s[x]];
             l.m.push_back((int)s.size());
             l.id.push_back(ids[i]);
         }
@@ -354,25 +360,11 @@ int launch_myers(apm_plan *pl, Bucket &b, const uint8_t *d_buf, long long buf_le
 }
 
 template <int MC>
-int launch_sliced_mc(apm_plan *pl, SlicedList &l, const SlicedArgs &base, long long nwin, cudaStream_t st) {
+int launch_sliced_mc(apm_plan *pl, SlicedList &l, SlicedArgs a, long long nwin, cudaStream_t st) {
     auto fn = sliced_count_kernel<MC>;
     const long long ntiles = (nwin + kSlicedTile - 1) / kSlicedTile;
-    // chunk size: as large as still allows the best occupancy the U table permits (3 CTAs/SM for the DNA
-    // alphabet), then shrunk until every resident CTA gets >= ~8 (chunk, tile) items
-    int dev_smem_sm = 0;
-    CUDA_TRY(cudaDeviceGetAttribute(&dev_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, pl->device));
-    const int max_ctas = MC == 64 ? 3 : 4;
-    int ppc = 1;
-    for (int ctas = max_ctas; ctas >= 1; --ctas) {
-        const long long budget = (long long)dev_smem_sm / ctas - 1024;  // 1 KB per CTA is reserved by the system
-        const long long room = budget - (long long)sliced_smem_bytes<MC>(0, pl->nplanes);
-        if (room >= (long long)8 * (MC + 12)) {
-            ppc = (int)std::min<long long>(128, room / (MC + 12));
-            break;
-        }
-    }
-    ppc = std::min(ppc, l.npat);
-    size_t smem = sliced_smem_bytes<MC>(ppc, pl->nplanes);
+    const int rowsU = sliced_rowsU(l.mmax);
+    const size_t smem = sliced_smem_bytes(pl->nplanes, rowsU);
     if (smem > l.smem_set) {
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         l.smem_set = smem;
@@ -381,14 +373,32 @@ int launch_sliced_mc(apm_plan *pl, SlicedList &l, const SlicedArgs &base, long l
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kSlicedThreads, smem));
     if (occ < 1) return fail(APM_ECUDA, "sliced kernel MC=%d does not fit an SM (smem %zu)", MC, smem);
     const long long capacity = (long long)pl->num_sms * occ;
-    const long long pattern_tiles = ntiles * l.npat;
-    ppc = (int)std::max<long long>(1, std::min<long long>(ppc, pattern_tiles / (8 * capacity)));
-    const long long nitems = ntiles * ((l.npat + ppc - 1) / ppc);
+    // work item = (tile, pattern range), handed out dynamically: ranges of >= 8 patterns (so the ~5 us of
+    // tile staging stay ~1 % of an item), >= ~64 items per resident CTA when the job is large enough
+    const long long max_splits = std::max<long long>(1, l.npat / 8);
+    const long long nsplits = std::max<long long>(1, std::min<long long>(max_splits, (64 * capacity + ntiles - 1) / ntiles));
+    const long long nitems = ntiles * nsplits;
     const unsigned gx = (unsigned)std::min<long long>(nitems, capacity);
-    const unsigned gy = 1;
-    SlicedArgs a = base;
-    a.pats_per_chunk = ppc;
-    fn<<<dim3(gx, gy), kSlicedThreads, smem, st>>>(a);
+    if (l.mmax > MC) {  // boundary deltas between the column blocks of long patterns
+        const size_t need = (size_t)(l.mmax + 2) * gx * kSlicedThreads * sizeof(uint2);
+        if (need > l.vscratch_bytes) {
+            if (l.d_vscratch) {
+                CUDA_TRY(cudaDeviceSynchronize());
+                CUDA_TRY(cudaFree(l.d_vscratch));
+                l.d_vscratch = nullptr;
+                l.vscratch_bytes = 0;
+            }
+            CUDA_TRY(cudaMalloc((void **)&l.d_vscratch, need));
+            l.vscratch_bytes = need;
+        }
+    }
+    if (!l.d_work) CUDA_TRY(cudaMalloc((void **)&l.d_work, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(l.d_work, 0, sizeof(unsigned long long), st));
+    a.work_counter = l.d_work;
+    a.vscratch = l.d_vscratch;
+    a.nsplits = (int)nsplits;
+    a.rowsU = rowsU;
+    fn<<<gx, kSlicedThreads, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     g_launches++;
     return APM_OK;
@@ -409,10 +419,14 @@ int launch_sliced(apm_plan *pl, SlicedList &l, const uint8_t *d_buf, long long b
     a.pat_id = l.d_id;
     a.plane_of = pl->d_plane_of;
     a.counts = pl->d_counts;
+    a.vscratch = nullptr;
     a.npat = l.npat;
-    a.pats_per_chunk = 0;
+    a.mcp = l.mcp;
     a.nplanes = pl->nplanes;
     a.k = pl->k;
+    a.nsplits = 1;
+    a.rowsU = 0;
+    a.work_counter = nullptr;
     return l.MC == 32 ? launch_sliced_mc<32>(pl, l, a, lim - w0, st) : launch_sliced_mc<64>(pl, l, a, lim - w0, st);
 }
 

@@ -39,7 +39,21 @@ constexpr int kSlicedThreads = 128;
 constexpr int kSlicedTile = 32 * kSlicedThreads;  // window starts per tile
 constexpr int kURowBytes = 136;                   // 34 words per U row: lanes hit distinct banks with LDS.64
 constexpr int kSlicedMaxPlanes = 8;               // symbols with their own occurrence plane
+constexpr int kSlicedMaxLen = 1024;               // longest pattern handled (column blocks of 64)
+constexpr int kSlicedTotPlanes = 12;              // bit-planes of the running distance sum (values <= 2*1024+k)
 constexpr uint8_t kNoPlane = 0xFF;
+
+// rows of one U plane for patterns up to mmax symbols: one per thread + the rows the halo reaches into
+__host__ __device__ inline int sliced_rowsU(int mmax) { return kSlicedTile / 32 + (mmax + 31) / 32 + 1; }
+// Shared-memory layout: [barrier | byte->plane map | B bit-vectors | U table].  The raw text tile is staged
+// by TMA INSIDE the (not yet built) U region, so it costs no extra shared memory and three CTAs fit an SM
+// for the 4-symbol DNA alphabet (76.5 KB each at m <= 224).
+__host__ __device__ inline size_t sliced_smem_fixed(int nplanes, int rowsU) {
+    return ((size_t)64 + 256 + (size_t)nplanes * (rowsU + 1) * 4 + 15) / 16 * 16;
+}
+__host__ __device__ inline size_t sliced_smem_bytes(int nplanes, int rowsU) {
+    return sliced_smem_fixed(nplanes, rowsU) + (size_t)nplanes * rowsU * kURowBytes;
+}
 
 #ifdef __CUDACC__
 
@@ -47,36 +61,17 @@ struct SlicedArgs {
     const uint8_t *buf;          // device text; buf[0] is global byte buf_offset
     long long buf_len, n_end;    // valid bytes; local index of the global end of text
     long long w0, w1;            // local window-start range
-    const uint8_t *pat_codes;    // [npat][MC] plane index of every pattern symbol (padded)
+    const uint8_t *pat_codes;    // [npat][mcp] plane index of every pattern symbol (zero padded, mcp >= m + 2)
     const int *pat_m;            // [npat]
     const int *pat_id;           // [npat] index into counts
     const uint8_t *plane_of;     // [256] byte -> plane index or kNoPlane
     unsigned long long *counts;
-    int npat, pats_per_chunk, nplanes, k;
+    uint2 *vscratch;             // [mmax + 2][gridDim.x * kSlicedThreads] boundary deltas between column blocks
+    int npat, mcp, nplanes, k;
+    int nsplits;                 // pattern ranges per tile (work item = tile x pattern range)
+    int rowsU;                   // rows per U plane
+    unsigned long long *work_counter;  // zeroed before the launch: dynamic (tile, range) item dispenser
 };
-
-// geometry shared by host and device
-__host__ __device__ constexpr int sliced_rowsU(int MC) { return kSlicedTile / 32 + MC / 32 + 1; }  // rows per U plane
-__host__ __device__ constexpr int sliced_nB(int MC) { return sliced_rowsU(MC) + 1; }  // words per bit-vector
-__host__ __device__ constexpr int sliced_span(int MC) { return sliced_nB(MC) * 32; }  // text positions per tile
-
-// Shared-memory layout: [barrier | byte->plane map | B bit-vectors | pattern chunk | U table].  The raw
-// text tile is staged by TMA INSIDE the (not yet built) U region, so it costs no extra shared memory and
-// three CTAs fit an SM for the 4-symbol DNA alphabet.
-template <int MC>
-__host__ __device__ inline size_t sliced_smem_fixed(int nplanes) {
-    size_t b = 64 + 256 + (size_t)nplanes * sliced_nB(MC) * 4;
-    return (b + 15) / 16 * 16;
-}
-template <int MC>
-__host__ __device__ inline size_t sliced_smem_chunk(int pats_per_chunk) {
-    return ((size_t)pats_per_chunk * (MC + 3 * sizeof(int)) + 16 + 15) / 16 * 16;
-}
-template <int MC>
-__host__ __device__ inline size_t sliced_smem_bytes(int pats_per_chunk, int nplanes) {
-    return sliced_smem_fixed<MC>(nplanes) + sliced_smem_chunk<MC>(pats_per_chunk) +
-           (size_t)nplanes * sliced_rowsU(MC) * kURowBytes;
-}
 
 // one LOP3: any boolean function of three words, LUT evaluated on a = 0xF0, b = 0xCC, c = 0xAA.
 // Written as PTX so that the five-instruction decomposition of a cell is exactly what gets executed
@@ -141,24 +136,34 @@ __device__ __forceinline__ void sliced_cell(uint32_t q, uint32_t &ap, uint32_t &
     am = vm;
 }
 
-// Row-major sweep of the m x m matrix for one pattern.  urow = this thread's row origin inside plane 0 of
-// the U table, pc = plane index of every pattern symbol (one readable byte past the end).
-// FULL (m == MC): branch-free, software pipelined -- the match words of the next column group (same row,
-// or the first group of the next row) are requested before the current group is computed.
-template <int MC, bool FULL>
+// Row-major sweep of one column block (MC columns starting at the column the pointer `urow` is positioned
+// on) over all `rows` pattern symbols.  urow = this thread's row origin inside plane 0 of the U table,
+// pc = plane index of every pattern symbol in global memory (readable up to rows + 1).
+// VIN / VOUT: the vertical deltas entering the block on its left edge are read from / those leaving on its
+// right edge are written to vs[row * vstride] (a per-thread column of a global scratch array, L2 resident);
+// without VIN the left edge is the DP boundary D[i][0] = i (+1).
+// FULL (all MC columns used): branch-free and software pipelined -- the match words of the next column
+// group (same row, or the first group of the next row) are requested before the current group is computed.
+template <int MC, bool FULL, bool VIN, bool VOUT>
 __device__ __forceinline__ void sliced_sweep(const unsigned char *__restrict__ urow, const uint8_t *__restrict__ pc,
-                                             int m, uint32_t plane_bytes, uint32_t (&hp)[MC], uint32_t (&hm)[MC]) {
+                                             int rows, int width, uint32_t plane_bytes, uint32_t (&hp)[MC],
+                                             uint32_t (&hm)[MC], uint2 *__restrict__ vs, long long vstride) {
+    uint32_t code_next = __ldg(pc + 1);
+    uint2 vin = make_uint2(0xFFFFFFFFu, 0u);
+    if constexpr (VIN) vin = vs[0];
     if constexpr (FULL) {
         constexpr int G = 8;  // columns per pipeline group: 4 LDS.64 in flight
         constexpr int NG = MC / G;
-        const unsigned char *e = urow + (uint32_t)pc[0] * plane_bytes;
+        const unsigned char *e = urow + (uint32_t)__ldg(pc) * plane_bytes;
         uint2 buf[G / 2];
 #pragma unroll
         for (int q = 0; q < G / 2; ++q) buf[q] = *reinterpret_cast<const uint2 *>(e + q * 8);
 #pragma unroll 1
-        for (int i = 0; i < MC; ++i) {
-            const unsigned char *e_next = urow + (uint32_t)pc[i + 1] * plane_bytes;
-            uint32_t ap = 0xFFFFFFFFu, am = 0u;  // D[i][0] - D[i-1][0] = +1
+        for (int i = 0; i < rows; ++i) {
+            const unsigned char *e_next = urow + code_next * plane_bytes;
+            code_next = __ldg(pc + i + 2);
+            uint32_t ap = vin.x, am = vin.y;  // left edge: boundary D[i][0] - D[i-1][0] = +1, or the previous block
+            if constexpr (VIN) vin = vs[(long long)(i + 1) * vstride];
 #pragma unroll
             for (int gi = 0; gi < NG; ++gi) {
                 uint2 cur[G / 2];
@@ -176,53 +181,69 @@ __device__ __forceinline__ void sliced_sweep(const unsigned char *__restrict__ u
                 for (int cc = 0; cc < G; ++cc)
                     sliced_cell((cc & 1) ? cur[cc >> 1].y : cur[cc >> 1].x, ap, am, hp[gi * G + cc], hm[gi * G + cc]);
             }
+            if constexpr (VOUT) vs[(long long)i * vstride] = make_uint2(ap, am);
             e = e_next;
         }
     } else {
         constexpr int CH = 8;  // columns per uniform early-exit check
 #pragma unroll 1
-        for (int i = 0; i < m; ++i) {
-            const unsigned char *e = urow + (uint32_t)pc[i] * plane_bytes;
-            uint32_t ap = 0xFFFFFFFFu, am = 0u;
+        for (int i = 0; i < rows; ++i) {
+            const unsigned char *e = urow + (uint32_t)__ldg(pc + i) * plane_bytes;
+            uint32_t ap = vin.x, am = vin.y;
+            if constexpr (VIN) vin = vs[(long long)(i + 1) * vstride];
 #pragma unroll
             for (int c = 0; c < MC; c += 2) {
-                if ((c % CH) == 0 && c >= m) break;  // uniform: m is the same for the whole CTA
+                if ((c % CH) == 0 && c >= width) break;  // uniform: the same for the whole CTA
                 const uint2 eq = *reinterpret_cast<const uint2 *>(e + (c >> 5) * kURowBytes + (c & 31) * 4);
                 sliced_cell(eq.x, ap, am, hp[c], hm[c]);
                 sliced_cell(eq.y, ap, am, hp[c + 1], hm[c + 1]);
             }
+            if constexpr (VOUT) vs[(long long)i * vstride] = make_uint2(ap, am);
         }
 #pragma unroll
-        for (int j = 0; j < MC; ++j)  // columns >= m: back to the neutral boundary value (they add a constant)
-            if (j >= m) { hp[j] = 0xFFFFFFFFu; hm[j] = 0u; }
+        for (int j = 0; j < MC; ++j)  // columns >= width: back to the neutral boundary value (they add a constant)
+            if (j >= width) { hp[j] = 0xFFFFFFFFu; hm[j] = 0u; }
     }
 }
 
+// tot += acc (bit-sliced): acc has NA planes, tot kSlicedTotPlanes
+template <int NA>
+__device__ __forceinline__ void planes_add(uint32_t (&tot)[kSlicedTotPlanes], const uint32_t (&acc)[NA]) {
+    uint32_t carry = 0u;
+#pragma unroll
+    for (int l = 0; l < kSlicedTotPlanes; ++l) {
+        if (l < NA) carry = plane_fa(tot[l], acc[l], carry);
+        else {
+            const uint32_t t = tot[l];
+            tot[l] = t ^ carry;
+            carry = t & carry;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent count kernel.  Work item = (text tile, pattern range): the tile's U table is built once per
+// item and every pattern of the range is swept over it; pattern symbols are streamed from global memory
+// (uniform addresses, L1 broadcast).  MC = columns per register block: 32 (patterns m <= 32, one block)
+// or 64 (any m <= kSlicedMaxLen, ceil(m/64) blocks chained through the global boundary scratch).
+// ------------------------------------------------------------------------------------------------
 template <int MC>
 __global__ void __launch_bounds__(kSlicedThreads, MC == 64 ? 3 : 4) sliced_count_kernel(const SlicedArgs a) {
     static_assert(MC == 32 || MC == 64, "MC must be 32 or 64");
-    constexpr int LOG = MC == 32 ? 6 : 7;  // 2*MC planes are summed: value range [0, 2*MC]
+    constexpr int LOG = MC == 32 ? 6 : 7;  // 2*MC planes are summed per block: value range [0, 2*MC]
     constexpr int NL = LOG + 1;
     extern __shared__ __align__(128) unsigned char smem[];
 
     const int tid = threadIdx.x;
-    constexpr int nB = sliced_nB(MC);        // words per occurrence bit-vector
-    constexpr int rowsU = sliced_rowsU(MC);  // rows per U plane
+    const int rowsU = a.rowsU;
+    const int nB = rowsU + 1;  // words per occurrence bit-vector
     const size_t off_B = 64 + 256;
-    const size_t off_pc = sliced_smem_fixed<MC>(a.nplanes);
-    const size_t off_pm = off_pc + (((size_t)a.pats_per_chunk * MC + 16 + 3) & ~size_t(3));
-    const size_t off_pid = off_pm + sizeof(int) * a.pats_per_chunk;
-    const size_t off_cnt = off_pid + sizeof(int) * a.pats_per_chunk;
-    const size_t off_U = off_pc + sliced_smem_chunk<MC>(a.pats_per_chunk);
+    const size_t off_U = sliced_smem_fixed(a.nplanes, rowsU);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     uint8_t *s_map = smem + 64;
     uint32_t *s_B = reinterpret_cast<uint32_t *>(smem + off_B);
-    uint8_t *s_pc = smem + off_pc;
-    int *s_pm = reinterpret_cast<int *>(smem + off_pm);
-    int *s_pid = reinterpret_cast<int *>(smem + off_pid);
-    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + off_cnt);
     uint8_t *s_raw = smem + off_U;  // raw text tile, overwritten by the U table once the bit-vectors exist
-    const uint32_t plane_bytes = rowsU * kURowBytes;
+    const uint32_t plane_bytes = (uint32_t)rowsU * kURowBytes;
 
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -233,35 +254,26 @@ __global__ void __launch_bounds__(kSlicedThreads, MC == 64 ? 3 : 4) sliced_count
 
     const long long nwin = a.w1 - a.w0;
     const long long ntiles = (nwin + kSlicedTile - 1) / kSlicedTile;
-    constexpr int span = sliced_span(MC);
+    const int span = nB * 32;  // text positions covered by the bit-vectors of a tile
+    const long long vstride = (long long)gridDim.x * kSlicedThreads;
+    uint2 *vs = a.vscratch + ((long long)blockIdx.x * kSlicedThreads + tid);
     uint32_t phase = 0;
 
-    // Work items = (pattern chunk, text tile), chunk-major, dealt round-robin to the persistent CTAs.
-    const int nchunks = (a.npat + a.pats_per_chunk - 1) / a.pats_per_chunk;
-    const long long nitems = ntiles * nchunks;
-    int cur_chunk = -1, pcount = 0;
-    for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
-        const int chunk = (int)(it / ntiles);
-        const long long t = it % ntiles;
-        // the tile covers text positions [ts, ts + span); te clips it to the buffer
+    const long long nitems = ntiles * a.nsplits;
+    const int per_split = (a.npat + a.nsplits - 1) / a.nsplits;
+    __shared__ long long s_item;
+    for (;;) {
+        // dynamic scheduling: items are handed out in order by one global atomic counter, so a CTA that
+        // finishes early (short patterns, ragged tiles) simply takes the next item
+        if (tid == 0) s_item = (long long)atomicAdd(a.work_counter, 1ull);
+        __syncthreads();
+        const long long it = s_item;
+        if (it >= nitems) break;
+        const long long t = it / a.nsplits;
+        const int split = (int)(it % a.nsplits);
+        const int p_begin = split * per_split, p_end = min(a.npat, p_begin + per_split);
         const TileGeom g = tile_geometry(a.buf, a.buf_len, a.w0, t, kSlicedTile, span - kSlicedTile);
-        if (tid == 0) tile_issue(g, a.buf, s_raw, bar);  // TMA bulk copy; overlaps the chunk reload below
-        if (chunk != cur_chunk) {  // (re)load the chunk's patterns; thread i owns slot i of both loops
-            const int p0 = chunk * a.pats_per_chunk;
-            for (int i = tid; i < pcount; i += kSlicedThreads) {
-                const uint32_t c = s_cnt[i];
-                if (c) atomicAdd(&a.counts[s_pid[i]], (unsigned long long)c);
-            }
-            pcount = min(a.pats_per_chunk, a.npat - p0);
-            for (int i = tid; i < pcount; i += kSlicedThreads) {
-                s_pm[i] = a.pat_m[p0 + i];
-                s_pid[i] = a.pat_id[p0 + i];
-                s_cnt[i] = 0;
-            }
-            for (int i = tid; i < pcount * MC; i += kSlicedThreads) s_pc[i] = a.pat_codes[(size_t)p0 * MC + i];
-            if (tid < 16) s_pc[pcount * MC + tid] = 0;  // the row loop reads one code past the last row
-            cur_chunk = chunk;
-        }
+        if (tid == 0) tile_issue(g, a.buf, s_raw, bar);  // TMA bulk copy of the raw tile
         if (g.tb > g.ta) {
             mbar_wait(bar, phase);
             phase ^= 1u;
@@ -291,53 +303,64 @@ __global__ void __launch_bounds__(kSlicedThreads, MC == 64 ? 3 : 4) sliced_count
         }
         __syncthreads();
 
-        // ---- hot loop: patterns x rows x columns, 5 LOP3 per cell
+        // ---- hot loop: patterns x column blocks x rows x columns, 5 LOP3 per cell
         const long long tile_end = min(g.ts + (long long)kSlicedTile, a.w1);
         const long long jbase = g.ts + 32ll * tid;
         const unsigned char *urow = smem + off_U + (size_t)tid * kURowBytes;
-        for (int pi = 0; pi < pcount; ++pi) {
-            const int m = s_pm[pi];
+        for (int pi = p_begin; pi < p_end; ++pi) {
+            const int m = __ldg(a.pat_m + pi);
             const long long lim = min(tile_end, a.n_end - m + 1);  // full windows only
             const long long nvalid = lim - jbase;
             const uint32_t validmask = nvalid >= 32 ? 0xFFFFFFFFu : (nvalid <= 0 ? 0u : ((1u << (int)nvalid) - 1u));
             uint32_t hits = 0;
             if (validmask != 0u) {
-                uint32_t hp[MC], hm[MC];
+                const uint8_t *pc = a.pat_codes + (size_t)pi * a.mcp;
+                const int nblk = (m + MC - 1) / MC;
+                uint32_t tot[kSlicedTotPlanes];
 #pragma unroll
-                for (int j = 0; j < MC; ++j) { hp[j] = 0xFFFFFFFFu; hm[j] = 0u; }  // D[0][j] - D[0][j-1] = +1
-                const uint8_t *pc = s_pc + pi * MC;
-                if (m == MC) sliced_sweep<MC, true>(urow, pc, m, plane_bytes, hp, hm);
-                else sliced_sweep<MC, false>(urow, pc, m, plane_bytes, hp, hm);
-                // V = sum_j (h+[j] + ~h-[j]) = D[m][m] + 2 (MC - m), bit-sliced in acc[0..LOG-1] + pend[LOG]
-                uint32_t acc[NL], pend[NL];
+                for (int l = 0; l < kSlicedTotPlanes; ++l) tot[l] = 0u;
+#pragma unroll 1
+                for (int b = 0; b < nblk; ++b) {
+                    const int width = min(MC, m - b * MC);
+                    const unsigned char *ub = urow + (size_t)b * (MC / 32) * kURowBytes;  // MC columns = MC/32 U rows
+                    uint32_t hp[MC], hm[MC];
 #pragma unroll
-                for (int l = 0; l < NL; ++l) { acc[l] = 0u; pend[l] = 0u; }
-                SumPlanes<MC, 0, NL>::run(hp, hm, acc, pend);
-                acc[LOG] = pend[LOG];
-                // windows with V <= T
-                const int T = a.k + 2 * (MC - m);
-                uint32_t le;
-                if (T >= 2 * MC) le = 0xFFFFFFFFu;
-                else {
-                    uint32_t lt = 0u, eqm = 0xFFFFFFFFu;
-#pragma unroll
-                    for (int l = LOG; l >= 0; --l) {
-                        const uint32_t tb = ((T >> l) & 1) ? 0xFFFFFFFFu : 0u;
-                        lt |= eqm & ~acc[l] & tb;
-                        eqm &= ~(acc[l] ^ tb);
+                    for (int j = 0; j < MC; ++j) { hp[j] = 0xFFFFFFFFu; hm[j] = 0u; }  // D[0][j] - D[0][j-1] = +1
+                    if (MC == 32 || nblk == 1) {
+                        if (width == MC) sliced_sweep<MC, true, false, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride);
+                        else sliced_sweep<MC, false, false, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride);
+                    } else if (b == 0) {
+                        sliced_sweep<MC, true, false, true>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride);
+                    } else if (b < nblk - 1) {
+                        sliced_sweep<MC, true, true, true>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride);
+                    } else {
+                        if (width == MC) sliced_sweep<MC, true, true, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride);
+                        else sliced_sweep<MC, false, true, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride);
                     }
-                    le = lt | eqm;
+                    // block sum: sum_j (h+[j] + ~h-[j]) over the MC columns of the last row (unused ones add 2)
+                    uint32_t acc[NL], pend[NL];
+#pragma unroll
+                    for (int l = 0; l < NL; ++l) { acc[l] = 0u; pend[l] = 0u; }
+                    SumPlanes<MC, 0, NL>::run(hp, hm, acc, pend);
+                    acc[LOG] = pend[LOG];
+                    planes_add<NL>(tot, acc);
                 }
-                hits = __popc(le & validmask);
+                // total V = D[m][m] + 2 * (nblk * MC - m); windows with V <= T
+                // (clamped: V < 2^kSlicedTotPlanes - 1 always, so a huge k simply matches everything)
+                const int T = min(a.k + 2 * (nblk * MC - m), (1 << kSlicedTotPlanes) - 1);
+                uint32_t lt = 0u, eqm = 0xFFFFFFFFu;
+#pragma unroll
+                for (int l = kSlicedTotPlanes - 1; l >= 0; --l) {
+                    const uint32_t tb = ((T >> l) & 1) ? 0xFFFFFFFFu : 0u;
+                    lt |= eqm & ~tot[l] & tb;
+                    eqm &= ~(tot[l] ^ tb);
+                }
+                hits = __popc((lt | eqm) & validmask);
             }
             hits = __reduce_add_sync(0xFFFFFFFFu, hits);
-            if ((tid & 31) == 0 && hits) atomicAdd(&s_cnt[pi], hits);
+            if ((tid & 31) == 0 && hits) atomicAdd(&a.counts[__ldg(a.pat_id + pi)], (unsigned long long)hits);
         }
         __syncthreads();  // U (and the raw staging area inside it) free for the next item
-    }
-    for (int i = tid; i < pcount; i += kSlicedThreads) {
-        const uint32_t c = s_cnt[i];
-        if (c) atomicAdd(&a.counts[s_pid[i]], (unsigned long long)c);
     }
 }
 

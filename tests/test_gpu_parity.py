@@ -193,6 +193,29 @@ def test_myers_vs_dp_kernel_large_slice():
         assert apm_b200.count_matches(text, pats, k) == dp, kernel
 
 
+@pytest.mark.parametrize("m", [65, 100, 128, 129, 200, 256, 257, 500, 1000, 1024])
+def test_long_patterns_sliced_column_blocks_vs_dp(m):
+    """m > 64: the sliced kernel chains ceil(m/64) column blocks through the boundary scratch."""
+    text = bytearray(oracle.synth_text(0x5EED0001, 31337, 30_000).tobytes())
+    rng = np.random.default_rng(m)
+    p0 = bytearray(text[7000:7000 + m])
+    for _ in range(5):  # a copy with 5 substitutions elsewhere in the text
+        p0[int(rng.integers(0, m))] = ord("A")
+    text[20000:20000 + m] = p0
+    text = bytes(text)
+    pats = [bytes(text[7000:7000 + m]), bytes(p0), oracle.synth_text(0x5EED0003, m, m).tobytes(),
+            text[-(m // 2):] + b"ACGT" * (m // 8 + 1)]
+    k = 6
+    apm_b200.set_option("kernel", "dp")
+    want = apm_b200.count_matches(text, pats, k)
+    assert want[0] >= 2 or m > 1000
+    for kernel in ("sliced", "auto"):
+        apm_b200.set_option("kernel", kernel)
+        assert apm_b200.count_matches(text, pats, k) == want, kernel
+    if m <= 300:
+        assert oracle.count_matches(text, pats[:2], k) == want[:2]
+
+
 # ---------------------------------------------------------------------------------------------
 # device-resident API: shards with halo, unaligned buffers, tiles
 # ---------------------------------------------------------------------------------------------

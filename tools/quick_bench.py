@@ -34,12 +34,13 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     combos = []
     for kern in ("sliced", "myers"):
-        combos.append((64, 4, 64, "4", "512", 32 << 20, "0", kern))
-        combos.append((64, 4, 128, "4", "512", 32 << 20, "0", kern))
-        combos.append((32, 2, 64, "4", "512", 32 << 20, "0", kern))
-        combos.append((50, 0, 64, "4", "512", 32 << 20, "0", kern))
-        combos.append((48, 3, 64, "4", "512", 32 << 20, "0", kern))
-        combos.append((24, 2, 64, "4", "512", 32 << 20, "0", kern))
+        combos.append((64, 4, 256, "4", "512", 8 << 20, "0", kern))
+        combos.append((200, 10, 64, "1", "512", 2 << 20, "0", kern))
+        combos.append((128, 6, 64, "2", "512", 4 << 20, "0", kern))
+        combos.append((256, 10, 32, "1", "512", 2 << 20, "0", kern))
+        combos.append((32, 2, 256, "4", "512", 16 << 20, "0", kern))
+        combos.append((50, 0, 256, "4", "512", 8 << 20, "0", kern))
+    combos.append((1000, 20, 16, "1", "512", 1 << 20, "0", "sliced"))
     for m, k, P, rb, tile, slab, var, kern in combos:
         apm_b200.set_option("rblock", rb)
         apm_b200.set_option("tile", tile)
