@@ -247,6 +247,39 @@ def run_ours(args) -> None:
     cells_step = cells_full(slab, NB_PATTERNS, M) * world
     value = cells_step / (ms_step * 1e-3) / 1e9
 
+    # ---- exact band mode: same slabs, only the 2k+1 diagonals that can matter for D <= k.
+    #      Reported separately as EFFECTIVE GCUPS (cells of the reference DP per second, most never touched).
+    band = None
+    if not args.no_band:
+        apm_b200.set_option("mode", "band")
+        bplan = apm_b200.Plan(pats, K_ERR)
+        for i in range(3):
+            bplan.count_device(shard.data_ptr(), b0, b1 - b0, N_TOTAL, j0 + (i % nslabs) * slab, j0 + (i % nslabs) * slab + slab, stream)
+        sync_all()
+        b_e0, b_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b_e0.record()
+        for i in range(args.steps):
+            a = j0 + ((3 + i) % nslabs) * slab
+            bplan.count_device(shard.data_ptr(), b0, b1 - b0, N_TOTAL, a, a + slab, stream)
+        b_e1.record()
+        sync_all()
+        bms = b_e0.elapsed_time(b_e1) / args.steps
+        if world > 1:
+            t = torch.tensor([bms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            bms = float(t.item())
+        # parity of the two modes on identical slabs
+        plan.zero_counts(stream)
+        bplan.zero_counts(stream)
+        plan.count_device(shard.data_ptr(), b0, b1 - b0, N_TOTAL, j0, j0 + slab, stream)
+        bplan.count_device(shard.data_ptr(), b0, b1 - b0, N_TOTAL, j0, j0 + slab, stream)
+        same = plan.read_counts(stream) == bplan.read_counts(stream)
+        band = {"value": cells_step / (bms * 1e-3) / 1e9, "unit": "effective GCUPS", "ms_per_step": bms,
+                "counts_equal_direct": bool(same),
+                "note": "exact Ukkonen band (9 of 64 diagonals at k=4): (2k+1)*5+(k+1) = 50 LOP3 per row and 32 windows"}
+        bplan.close()
+        apm_b200.set_option("mode", "direct")
+
     # ---- end-to-end through the one-shot C-ABI call with HOST buffers ------------------------------
     e2e_windows = args.e2e_windows
     host_text = torch.empty(e2e_windows + M - 1, dtype=torch.uint8).pin_memory()
@@ -331,7 +364,7 @@ def run_ours(args) -> None:
                    "kernel": args.kernel, "mode": "direct", "shard": "db", "l2": "successive steps read successive "
                    "slabs of a 16 GiB text (inputs larger than L2)", "text_bytes_per_rank": int(b1 - b0)},
         "text_gbs": text_gbs, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-        "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "parity": parity,
+        "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "parity": parity, "band_mode": band,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -358,6 +391,7 @@ def main() -> None:
     ap.add_argument("--e2e-windows", type=int, default=1 << 20)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip cpu_baseline + parity spot check")
+    ap.add_argument("--no-band", action="store_true", help="skip the extra exact-band-mode measurement")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

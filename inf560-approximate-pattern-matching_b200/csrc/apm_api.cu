@@ -23,6 +23,7 @@
 #include "apm_dp.cuh"
 #include "apm_myers.cuh"
 #include "apm_sliced.cuh"
+#include "apm_band.cuh"
 #include "apm_util_kernels.cuh"
 
 using namespace apm;
@@ -51,7 +52,7 @@ int fail(int code, const char *fmt, ...) {
 
 enum { SHARD_AUTO = 0, SHARD_DB = 1, SHARD_PATTERNS = 2 };
 enum { KERNEL_AUTO = 0, KERNEL_MYERS = 1, KERNEL_DP = 2, KERNEL_SLICED = 3 };
-enum { MODE_DIRECT = 0, MODE_FILTER = 1 };
+enum { MODE_DIRECT = 0, MODE_BAND = 1 };
 
 struct Options {
     int gpus = 1;  // 0 = all
@@ -398,6 +399,49 @@ int launch_sliced_mc(apm_plan *pl, SlicedList &l, SlicedArgs a, long long nwin, 
     a.vscratch = l.d_vscratch;
     a.nsplits = (int)nsplits;
     a.rowsU = rowsU;
+    a.row_bytes = kURowBytes;
+    a.row_cols = 32;
+    fn<<<gx, kSlicedThreads, smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    g_launches++;
+    return APM_OK;
+}
+
+// smallest instantiated band half-width >= k
+using BandKernel = void (*)(const SlicedArgs);
+BandKernel pick_band(int k, int *K_out) {
+#define APM_BAND_CASE(KK) if (k <= KK) { *K_out = KK; return band_count_kernel<KK>; }
+    APM_BAND_CASE(0) APM_BAND_CASE(1) APM_BAND_CASE(2) APM_BAND_CASE(3) APM_BAND_CASE(4) APM_BAND_CASE(5)
+    APM_BAND_CASE(6) APM_BAND_CASE(8) APM_BAND_CASE(10) APM_BAND_CASE(12) APM_BAND_CASE(16)
+#undef APM_BAND_CASE
+    *K_out = -1;
+    return nullptr;
+}
+
+int launch_band(apm_plan *pl, SlicedList &l, SlicedArgs a, long long nwin, cudaStream_t st) {
+    int K = -1;
+    BandKernel fn = pick_band(pl->k, &K);
+    const long long ntiles = (nwin + kSlicedTile - 1) / kSlicedTile;
+    const int rowsU = sliced_rowsU(l.mmax + K) + 1;  // the band reaches K columns past the window; +1 lead row
+    const int row_cols = 32 + 2 * K;
+    const int row_bytes = 4 * (row_cols | 1);      // odd number of words: conflict-free LDS.32 across lanes
+    const size_t smem = sliced_smem_bytes(pl->nplanes, rowsU, row_bytes);
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kSlicedThreads, smem));
+    if (occ < 1) return fail(APM_ECUDA, "band kernel K=%d does not fit an SM (smem %zu)", K, smem);
+    const long long capacity = (long long)pl->num_sms * occ;
+    const long long max_splits = std::max<long long>(1, l.npat / 32);
+    const long long nsplits = std::max<long long>(1, std::min<long long>(max_splits, (64 * capacity + ntiles - 1) / ntiles));
+    const unsigned gx = (unsigned)std::min<long long>(ntiles * nsplits, capacity);
+    if (!l.d_work) CUDA_TRY(cudaMalloc((void **)&l.d_work, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(l.d_work, 0, sizeof(unsigned long long), st));
+    a.work_counter = l.d_work;
+    a.nsplits = (int)nsplits;
+    a.rowsU = rowsU;
+    a.row_bytes = row_bytes;
+    a.row_cols = row_cols;
+    a.lead = 32;
     fn<<<gx, kSlicedThreads, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     g_launches++;
@@ -426,7 +470,14 @@ int launch_sliced(apm_plan *pl, SlicedList &l, const uint8_t *d_buf, long long b
     a.k = pl->k;
     a.nsplits = 1;
     a.rowsU = 0;
+    a.row_bytes = kURowBytes;
+    a.row_cols = 32;
+    a.lead = 0;
     a.work_counter = nullptr;
+    // exact band mode: only the 2K+1 diagonals that can matter for D <= k (worth it when the band is
+    // narrower than the matrix)
+    if (pl->opt.mode == MODE_BAND && pl->k <= kBandMaxK && 2 * pl->k + 1 < l.mmin)
+        return launch_band(pl, l, a, lim - w0, st);
     return l.MC == 32 ? launch_sliced_mc<32>(pl, l, a, lim - w0, st) : launch_sliced_mc<64>(pl, l, a, lim - w0, st);
 }
 
@@ -562,7 +613,8 @@ int apm_set_option(const char *key, const char *value) {
         else return bad();
     } else if (k == "mode") {
         if (v == "direct") g_opt.mode = MODE_DIRECT;
-        else return bad();  // "filter" is not built yet
+        else if (v == "band") g_opt.mode = MODE_BAND;
+        else return bad();
     } else if (k == "rblock") {
         if (v == "auto") g_opt.rblock = 0;
         else if (v == "1" || v == "2" || v == "4") g_opt.rblock = atoi(value);
@@ -595,7 +647,7 @@ const char *apm_get_option(const char *key) {
     else if (k == "shard") tl_optbuf = o.shard == SHARD_DB ? "db" : (o.shard == SHARD_PATTERNS ? "patterns" : "auto");
     else if (k == "kernel")
         tl_optbuf = o.kernel == KERNEL_DP ? "dp" : (o.kernel == KERNEL_MYERS ? "myers" : (o.kernel == KERNEL_SLICED ? "sliced" : "auto"));
-    else if (k == "mode") tl_optbuf = "direct";
+    else if (k == "mode") tl_optbuf = o.mode == MODE_BAND ? "band" : "direct";
     else if (k == "rblock") tl_optbuf = o.rblock ? std::to_string(o.rblock) : "auto";
     else if (k == "tile") tl_optbuf = o.tile ? std::to_string(o.tile) : "auto";
     else if (k == "variant") tl_optbuf = std::to_string(o.variant);

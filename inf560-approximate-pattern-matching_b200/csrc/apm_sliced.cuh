@@ -49,10 +49,10 @@ __host__ __device__ inline int sliced_rowsU(int mmax) { return kSlicedTile / 32 
 // by TMA INSIDE the (not yet built) U region, so it costs no extra shared memory and three CTAs fit an SM
 // for the 4-symbol DNA alphabet (76.5 KB each at m <= 224).
 __host__ __device__ inline size_t sliced_smem_fixed(int nplanes, int rowsU) {
-    return ((size_t)64 + 256 + (size_t)nplanes * (rowsU + 1) * 4 + 15) / 16 * 16;
+    return ((size_t)64 + 256 + (size_t)nplanes * (rowsU + 2) * 4 + 15) / 16 * 16;
 }
-__host__ __device__ inline size_t sliced_smem_bytes(int nplanes, int rowsU) {
-    return sliced_smem_fixed(nplanes, rowsU) + (size_t)nplanes * rowsU * kURowBytes;
+__host__ __device__ inline size_t sliced_smem_bytes(int nplanes, int rowsU, int row_bytes = kURowBytes) {
+    return sliced_smem_fixed(nplanes, rowsU) + (size_t)nplanes * rowsU * row_bytes;
 }
 
 #ifdef __CUDACC__
@@ -70,6 +70,9 @@ struct SlicedArgs {
     int npat, mcp, nplanes, k;
     int nsplits;                 // pattern ranges per tile (work item = tile x pattern range)
     int rowsU;                   // rows per U plane
+    int row_bytes;               // bytes per U row (kURowBytes; wider for the band kernel)
+    int row_cols;                // 32-bit windows stored per U row (32; 32 + 2K for the band kernel)
+    int lead;                    // text positions staged BEFORE the tile start (0; 32 for the band kernel)
     unsigned long long *work_counter;  // zeroed before the launch: dynamic (tile, range) item dispenser
 };
 
@@ -221,6 +224,57 @@ __device__ __forceinline__ void planes_add(uint32_t (&tot)[kSlicedTotPlanes], co
     }
 }
 
+// Stage text tile t: TMA bulk copy of the raw bytes into the (not yet built) U region, occurrence
+// bit-vectors by warp ballots, then the U table.  Returns the tile geometry; ends with a __syncthreads().
+__device__ __forceinline__ TileGeom sliced_stage_tile(const SlicedArgs &a, long long t, unsigned char *smem,
+                                                      uint64_t *bar, uint32_t &phase) {
+    const int tid = threadIdx.x;
+    const int rowsU = a.rowsU;
+    const int nB = rowsU + 2;  // words per occurrence bit-vector
+    const int span = nB * 32;  // text positions covered by the bit-vectors of a tile
+    const size_t off_U = sliced_smem_fixed(a.nplanes, rowsU);
+    const uint8_t *s_map = smem + 64;
+    uint32_t *s_B = reinterpret_cast<uint32_t *>(smem + 64 + 256);
+    uint8_t *s_raw = smem + off_U;  // raw text tile, overwritten by the U table once the bit-vectors exist
+    const uint32_t plane_bytes = (uint32_t)rowsU * a.row_bytes;
+
+    // the staged range starts `lead` positions before the tile (positions before the buffer hold no symbol)
+    TileGeom g = tile_geometry(a.buf, a.buf_len, a.w0 - a.lead, t, kSlicedTile, span - kSlicedTile);
+    if (tid == 0) tile_issue(g, a.buf, s_raw, bar);  // TMA bulk copy of the raw tile
+    if (g.tb > g.ta) {
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+    }
+    // ---- occurrence bit-vectors: bit x of B[p] <-> text position ts + x holds the symbol of plane p.
+    //      Bytes outside the TMA box (<= 15 on either side) are read from global memory.
+    {
+        const int lane = tid & 31;
+        for (int w = tid >> 5; w < nB; w += kSlicedThreads / 32) {
+            const long long i = g.ts + 32 * w + lane;
+            uint32_t c = kNoPlane;
+            if (i >= 0 && i < g.te) c = s_map[(i >= g.ta && i < g.tb) ? s_raw[i - g.a0] : a.buf[i]];
+            for (int p = 0; p < a.nplanes; ++p) {
+                const uint32_t bits = __ballot_sync(0xFFFFFFFFu, c == (uint32_t)p);
+                if (lane == 0) s_B[p * nB + w] = bits;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- U table: U[p][w][s] = bits [32 w + s, +32) of B[p], s < row_cols (columns >= 32 repeat the start
+    //      of the next row, so a run of row_cols - 32 + 1 consecutive offsets never has to change rows)
+    for (int idx = tid; idx < a.nplanes * rowsU; idx += kSlicedThreads) {
+        const int p = idx / rowsU, w = idx - p * rowsU;
+        const uint32_t b0 = s_B[p * nB + w], b1 = s_B[p * nB + w + 1], b2 = s_B[p * nB + w + 2];
+        uint32_t *dst = reinterpret_cast<uint32_t *>(smem + off_U + (size_t)p * plane_bytes + (size_t)w * a.row_bytes);
+#pragma unroll
+        for (int s = 0; s < 32; ++s) dst[s] = __funnelshift_r(b0, b1, s);
+        for (int s = 32; s < a.row_cols; ++s) dst[s] = __funnelshift_r(b1, b2, s - 32);
+    }
+    __syncthreads();
+    g.ts += a.lead;  // report the tile start proper
+    return g;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Persistent count kernel.  Work item = (text tile, pattern range): the tile's U table is built once per
 // item and every pattern of the range is swept over it; pattern symbols are streamed from global memory
@@ -236,13 +290,9 @@ __global__ void __launch_bounds__(kSlicedThreads, MC == 64 ? 3 : 4) sliced_count
 
     const int tid = threadIdx.x;
     const int rowsU = a.rowsU;
-    const int nB = rowsU + 1;  // words per occurrence bit-vector
-    const size_t off_B = 64 + 256;
     const size_t off_U = sliced_smem_fixed(a.nplanes, rowsU);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     uint8_t *s_map = smem + 64;
-    uint32_t *s_B = reinterpret_cast<uint32_t *>(smem + off_B);
-    uint8_t *s_raw = smem + off_U;  // raw text tile, overwritten by the U table once the bit-vectors exist
     const uint32_t plane_bytes = (uint32_t)rowsU * kURowBytes;
 
     if (tid == 0) {
@@ -254,7 +304,6 @@ __global__ void __launch_bounds__(kSlicedThreads, MC == 64 ? 3 : 4) sliced_count
 
     const long long nwin = a.w1 - a.w0;
     const long long ntiles = (nwin + kSlicedTile - 1) / kSlicedTile;
-    const int span = nB * 32;  // text positions covered by the bit-vectors of a tile
     const long long vstride = (long long)gridDim.x * kSlicedThreads;
     uint2 *vs = a.vscratch + ((long long)blockIdx.x * kSlicedThreads + tid);
     uint32_t phase = 0;
@@ -272,36 +321,7 @@ __global__ void __launch_bounds__(kSlicedThreads, MC == 64 ? 3 : 4) sliced_count
         const long long t = it / a.nsplits;
         const int split = (int)(it % a.nsplits);
         const int p_begin = split * per_split, p_end = min(a.npat, p_begin + per_split);
-        const TileGeom g = tile_geometry(a.buf, a.buf_len, a.w0, t, kSlicedTile, span - kSlicedTile);
-        if (tid == 0) tile_issue(g, a.buf, s_raw, bar);  // TMA bulk copy of the raw tile
-        if (g.tb > g.ta) {
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-        }
-        // ---- occurrence bit-vectors: bit x of B[p] <-> text position ts + x holds the symbol of plane p.
-        //      Bytes outside the TMA box (<= 15 on either side) are read from global memory.
-        {
-            const int lane = tid & 31;
-            for (int w = tid >> 5; w < nB; w += kSlicedThreads / 32) {
-                const long long i = g.ts + 32 * w + lane;
-                uint32_t c = kNoPlane;
-                if (i < g.te) c = s_map[(i >= g.ta && i < g.tb) ? s_raw[i - g.a0] : a.buf[i]];
-                for (int p = 0; p < a.nplanes; ++p) {
-                    const uint32_t bits = __ballot_sync(0xFFFFFFFFu, c == (uint32_t)p);
-                    if (lane == 0) s_B[p * nB + w] = bits;
-                }
-            }
-        }
-        __syncthreads();
-        // ---- U table: U[p][w][s] = bits [32 w + s, +32) of B[p]
-        for (int idx = tid; idx < a.nplanes * rowsU; idx += kSlicedThreads) {
-            const int p = idx / rowsU, w = idx - p * rowsU;
-            const uint32_t lo = s_B[p * nB + w], hi = s_B[p * nB + w + 1];
-            uint32_t *dst = reinterpret_cast<uint32_t *>(smem + off_U + (size_t)p * plane_bytes + (size_t)w * kURowBytes);
-#pragma unroll
-            for (int s = 0; s < 32; ++s) dst[s] = __funnelshift_r(lo, hi, s);
-        }
-        __syncthreads();
+        const TileGeom g = sliced_stage_tile(a, t, smem, bar, phase);
 
         // ---- hot loop: patterns x column blocks x rows x columns, 5 LOP3 per cell
         const long long tile_end = min(g.ts + (long long)kSlicedTile, a.w1);

@@ -31,7 +31,7 @@ __device__ __forceinline__ TileGeom tile_geometry(const uint8_t *buf, long long 
     g.te = g.ts + tile + halo;
     if (g.te > buf_len) g.te = buf_len;
     g.a0 = g.ts - (long long)((reinterpret_cast<uintptr_t>(buf) + (uintptr_t)g.ts) & 15);
-    g.ta = g.a0 < 0 ? g.a0 + 16 : g.a0;
+    g.ta = g.a0 < 0 ? g.a0 + ((-g.a0 + 15) / 16) * 16 : g.a0;  // first 16-byte aligned byte inside the buffer
     g.tb = g.a0 + ((g.te - g.a0 + 15) / 16) * 16;
     if (g.tb > buf_len) g.tb -= 16;
     return g;

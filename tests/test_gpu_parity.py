@@ -20,7 +20,7 @@ CASES = cases()
 @pytest.fixture(autouse=True)
 def _default_options():
     for k, v in (("kernel", "auto"), ("rblock", "auto"), ("tile", "auto"), ("gpus", "1"), ("shard", "auto"),
-                 ("variant", "0")):
+                 ("variant", "0"), ("mode", "direct")):
         apm_b200.set_option(k, v)
     yield
 
@@ -81,6 +81,53 @@ def test_random_vs_oracle_step_variants(seed, variant):
     apm_b200.set_option("kernel", "myers")
     apm_b200.set_option("variant", variant)
     assert apm_b200.count_matches(text, pats, k) == oracle.count_matches(text, pats, k)
+
+
+# ---------------------------------------------------------------------------------------------
+# exact band mode (Ukkonen band): bit-identical to the full evaluation
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c["name"])
+def test_golden_band_mode(case):
+    apm_b200.set_option("mode", "band")
+    assert apm_b200.count_matches(FX[case["text"]], case["patterns"], case["k"]) == case["expected"]
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_vs_oracle_band_mode(seed):
+    rng = np.random.default_rng(5000 + seed)
+    text, pats, k = _random_case(rng)
+    apm_b200.set_option("mode", "band")
+    assert apm_b200.count_matches(text, pats, k) == oracle.count_matches(text, pats, k)
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16, 17])
+def test_band_mode_every_band_width(k):
+    """Every instantiated band half-width (and k = 17: falls back to the full kernel), distances around k."""
+    n = 60_000
+    base = bytearray(oracle.synth_text(0x5EED0001, 1234, n).tobytes())
+    rng = np.random.default_rng(k)
+    pats = []
+    for idx, m in enumerate((40, 64, 100, 200)):
+        p = bytes(base[3000 * (idx + 1):3000 * (idx + 1) + m])
+        pats.append(p)
+        for e in range(0, k + 3):  # plant copies with e edits (substitutions, an insertion+deletion pair)
+            q = bytearray(p)
+            for _ in range(e):
+                q[int(rng.integers(0, m))] = int(rng.choice(list(b"ACGT")))
+            if e >= 2:
+                pos = int(rng.integers(1, m - 2))
+                del q[pos]
+                q.insert(int(rng.integers(1, m - 2)), ord("A"))
+            off = 20000 + 2000 * idx + 300 * e
+            base[off:off + m] = q
+    text = bytes(base)
+    apm_b200.set_option("kernel", "dp")
+    want = apm_b200.count_matches(text, pats, k)
+    apm_b200.set_option("kernel", "auto")
+    assert apm_b200.count_matches(text, pats, k) == want
+    apm_b200.set_option("mode", "band")
+    assert apm_b200.count_matches(text, pats, k) == want
+    assert sum(want) > 0
 
 
 def test_cli_drop_in(tmp_path):

@@ -33,19 +33,18 @@ def main():
     torch.cuda.synchronize()
     st = torch.cuda.current_stream().cuda_stream
     combos = []
-    for kern in ("sliced", "myers"):
-        combos.append((64, 4, 256, "4", "512", 8 << 20, "0", kern))
-        combos.append((200, 10, 64, "1", "512", 2 << 20, "0", kern))
-        combos.append((128, 6, 64, "2", "512", 4 << 20, "0", kern))
-        combos.append((256, 10, 32, "1", "512", 2 << 20, "0", kern))
-        combos.append((32, 2, 256, "4", "512", 16 << 20, "0", kern))
-        combos.append((50, 0, 256, "4", "512", 8 << 20, "0", kern))
-    combos.append((1000, 20, 16, "1", "512", 1 << 20, "0", "sliced"))
-    for m, k, P, rb, tile, slab, var, kern in combos:
+    for mode in ("band", "direct"):
+        combos.append((64, 4, 256, "4", "512", 16 << 20, "0", "auto", mode))
+        combos.append((200, 10, 64, "1", "512", 4 << 20, "0", "auto", mode))
+        combos.append((32, 2, 256, "4", "512", 32 << 20, "0", "auto", mode))
+        combos.append((64, 8, 256, "4", "512", 16 << 20, "0", "auto", mode))
+        combos.append((1000, 16, 16, "1", "512", 2 << 20, "0", "auto", mode))
+    for m, k, P, rb, tile, slab, var, kern, mode in combos:
         apm_b200.set_option("rblock", rb)
         apm_b200.set_option("tile", tile)
         apm_b200.set_option("variant", var)
         apm_b200.set_option("kernel", kern)
+        apm_b200.set_option("mode", mode)
         pats, _, _ = make_patterns(TEXT_SEED, n, P, m, 7)
         with apm_b200.Plan(pats, k) as plan:
             def step(i):
@@ -65,7 +64,7 @@ def main():
             nw = (m + 31) // 32
             cells = slab * P * m * m
             ops = slab * P * m * nw * 10
-            print(json.dumps({"m": m, "k": k, "P": P, "kernel": kern, "rblock": rb, "tile": tile, "variant": var, "slab": slab, "ms": ms,
+            print(json.dumps({"m": m, "k": k, "P": P, "kernel": kern, "mode": mode, "rblock": rb, "tile": tile, "variant": var, "slab": slab, "ms": ms,
                               "GCUPS": cells / ms / 1e6, "Tiops": ops / ms / 1e9,
                               "frac_of_lop3_iadd3_peak": ops / (ms * 1e-3) / peaks["lop3+iadd3"]}), flush=True)
 
