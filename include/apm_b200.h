@@ -62,12 +62,16 @@ int apm_count_matches_file(const char *path, const char *const *patterns, const 
 /* Options (process-wide, read when a call starts):
  *   "gpus"    = "1".."8" | "all"      devices used by the one-shot API (default 1)
  *   "shard"   = "db" | "patterns" | "auto"   how work is split over several GPUs (default auto)
- *   "kernel"  = "myers" | "dp"        myers: bit-parallel kernel + DP for tails/long patterns
- *                                     (default); dp: explicit-DP kernel for everything
- *   "mode"    = "direct" | "filter"   direct: every window is evaluated in full (default);
- *                                     filter: exact semi-global pre-filter + verification
- *   "rblock"  = "1" | "2" | "4" | "auto"     patterns register-blocked per thread
- *   "tile"    = window starts per CTA tile (multiple of 256) or "auto"
+ *   "kernel"  = "auto" | "sliced" | "myers" | "dp"
+ *                 auto (default): window-sliced bit-parallel kernel (m <= 1024, <= 8 pattern symbols),
+ *                 row-parallel Hyyro/Myers kernel otherwise (m <= 256), explicit DP for the rest;
+ *                 every mode routes the truncated tail windows to the explicit-DP kernel;
+ *                 dp: explicit-DP kernel for everything (in-GPU cross-check)
+ *   "mode"    = "direct" | "band"     direct (default): every DP cell of every window is evaluated;
+ *                                     band: exact Ukkonen band |i-j| <= k (same counts, ~(2k+1)/m of the work)
+ *   "rblock"  = "1" | "2" | "4" | "auto"     patterns register-blocked per thread (row-parallel kernel)
+ *   "tile"    = window starts per CTA tile (multiple of 256) or "auto"   (row-parallel kernel)
+ *   "variant" = "0" | "1" | "2"       column-step code variant of the row-parallel kernel
  * Unknown key / value -> APM_EINVAL.                                                              */
 int apm_set_option(const char *key, const char *value);
 const char *apm_get_option(const char *key);

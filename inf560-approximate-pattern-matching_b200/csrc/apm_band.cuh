@@ -31,6 +31,11 @@ constexpr int kBandMaxK = 16;
 
 #ifdef __CUDACC__
 
+// address of the match word of text offset c0 inside a U plane row (c0 may be negative: previous row)
+__device__ __forceinline__ const unsigned char *band_row_ptr(const unsigned char *plane_row, int c0, int row_bytes) {
+    return plane_row + (c0 >> 5) * row_bytes + (c0 & 31) * 4;
+}
+
 template <int K>
 __global__ void __launch_bounds__(kSlicedThreads, 3) band_count_kernel(const SlicedArgs a) {
     constexpr int BW = 2 * K + 1;
@@ -85,24 +90,37 @@ __global__ void __launch_bounds__(kSlicedThreads, 3) band_count_kernel(const Sli
                     hbp[d] = d > K ? 0xFFFFFFFFu : 0u;
                     hbm[d] = d > K ? 0u : 0xFFFFFFFFu;
                 }
-                uint32_t T[K + 1];  // T[q] = (number of non-free diagonal steps so far) > q
+                // T[q] = (K - k + number of non-free diagonal steps so far) > q: starting the count at K - k makes
+                // the final test "count > k" the compile-time plane T[K] whatever the runtime k <= K is
+                uint32_t T[K + 1];
 #pragma unroll
-                for (int q = 0; q <= K; ++q) T[q] = 0u;
+                for (int q = 0; q <= K; ++q) T[q] = q < K - a.k ? 0xFFFFFFFFu : 0u;
                 uint32_t code_next = __ldg(pc + 1);
-                const unsigned char *e = urow + (uint32_t)__ldg(pc) * plane_bytes;
+                // match words of band index 0..2K of row i: text offset c0 = i - K (negative in the first K
+                // rows: left continuation, read through the tail of the previous U row); U rows hold 32 + 2K
+                // windows, so the 2K+1 words never change rows: one row pointer + immediate offsets
+                uint32_t qn[BW];  // software pipeline: the words of the NEXT row are requested a row ahead
+                {
+                    const unsigned char *rp = band_row_ptr(urow + (uint32_t)__ldg(pc) * plane_bytes, -K, row_bytes);
+#pragma unroll
+                    for (int d = 0; d < BW; ++d) qn[d] = *reinterpret_cast<const uint32_t *>(rp + 4 * d);
+                }
 #pragma unroll 1
                 for (int i = 0; i < m; ++i) {  // row i+1 of the DP; band index d <-> text offset c = i + d - K
-                    const unsigned char *e_next = urow + code_next * plane_bytes;
+                    uint32_t qc[BW];
+#pragma unroll
+                    for (int d = 0; d < BW; ++d) qc[d] = qn[d];
+                    {
+                        const unsigned char *rp = band_row_ptr(urow + code_next * plane_bytes, i + 1 - K, row_bytes);
+#pragma unroll
+                        for (int d = 0; d < BW; ++d) qn[d] = *reinterpret_cast<const uint32_t *>(rp + 4 * d);
+                    }
                     code_next = __ldg(pc + i + 2);
                     uint32_t ap = 0xFFFFFFFFu, am = 0u;  // left of the band: +1 (boundary or out-of-band)
                     uint32_t z = 0u;
-                    // text offset of band index 0 (negative in the first K rows: left continuation, read from
-                    // the previous U row); U rows hold 32 + 2K windows, so the 2K+1 cells never change rows
-                    const int c0 = i - K;
-                    const unsigned char *rp = e + (c0 >> 5) * row_bytes + (c0 & 31) * 4;
 #pragma unroll
                     for (int d = 0; d < BW; ++d) {
-                        const uint32_t q = *reinterpret_cast<const uint32_t *>(rp + 4 * d);
+                        const uint32_t q = qc[d];
                         const uint32_t bp = d + 1 < BW ? hbp[d + 1] : 0xFFFFFFFFu;  // above the band: +1
                         const uint32_t bm = d + 1 < BW ? hbm[d + 1] : 0u;
                         const uint32_t d0 = lop3<kLutOr3>(q, am, bm);
@@ -117,14 +135,9 @@ __global__ void __launch_bounds__(kSlicedThreads, 3) band_count_kernel(const Sli
 #pragma unroll
                     for (int q = K; q >= 1; --q) T[q] |= T[q - 1] & z;
                     T[0] |= z;
-                    e = e_next;
                 }
-                // D[m][m] <= k  <=>  not (count > k); the runtime k is <= K
-                uint32_t over = 0xFFFFFFFFu;
-#pragma unroll
-                for (int q = 0; q <= K; ++q)
-                    if (q == a.k) over = T[q];
-                hits = __popc(~over & validmask);
+                // D[m][m] <= k  <=>  not (count > k)
+                hits = __popc(~T[K] & validmask);
             }
             hits = __reduce_add_sync(0xFFFFFFFFu, hits);
             if ((tid & 31) == 0 && hits) atomicAdd(&a.counts[__ldg(a.pat_id + pi)], (unsigned long long)hits);
