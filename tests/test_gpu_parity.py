@@ -466,3 +466,19 @@ def test_dist_layer_nccl_two_gpus():
     want = apm_b200.count_matches(text.tobytes(), pats, 3)
     for rank, out in res:
         assert out["db"] == want and out["patterns"] == want
+
+
+def test_one_shot_api_two_gpus_single_process():
+    """gpus=2 inside ONE process (the C launcher drives both devices): DB shards and pattern shards."""
+    torch = _torch()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    text = oracle.synth_text(0x5EED0001, 2024, 3_000_000).tobytes()
+    pats = [text[i * 40009:i * 40009 + m] for i, m in enumerate([64, 64, 50, 32, 200, 64, 100])] + [text[-33:] + b"ACGT"]
+    k = 3
+    apm_b200.set_option("gpus", "1")
+    want = apm_b200.count_matches(text, pats, k)
+    apm_b200.set_option("gpus", "2")
+    for shard in ("db", "patterns", "auto"):
+        apm_b200.set_option("shard", shard)
+        assert apm_b200.count_matches(text, pats, k) == want, shard
