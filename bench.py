@@ -324,9 +324,20 @@ def run_ours(args) -> None:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     text_gbs = slab * world / (ms_step * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this very
+    # configuration (profiles/traffic.json); null when the bench runs a configuration that was not captured
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tr = json.load(f).get("sliced_count_kernel<64>", {})
+        if args.kernel in ("auto", "sliced") and tr.get("slab_windows") == slab and tr.get("patterns") == NB_PATTERNS:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    algorithmic_bytes = slab + (M - 1) + NB_PATTERNS * (M + 16) + 8 * NB_PATTERNS  # text + halo + patterns + counts
     roofline = {
         "bound": "int_alu", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tiop/s",
-        "frac": achieved / int_peak, "traffic": None,
+        "frac": achieved / int_peak, "traffic": traffic, "algorithmic_bytes": algorithmic_bytes,
         "kernel": "sliced_count_kernel<64>" if args.kernel in ("auto", "sliced") else "myers_count_kernel<2,4,0>",
         "algorithmic_ops_per_unit": "10*m*ceil(m/32) = 1280 int32 ops per (pattern, window), SURVEY.md 8d",
         "peak_source": "measured in this run: max(LOP3+IADD3, LOP3+IMAD) dependency-free microbenchmark",
