@@ -69,6 +69,12 @@ int apm_count_matches_file(const char *path, const char *const *patterns, const 
  *                 dp: explicit-DP kernel for everything (in-GPU cross-check)
  *   "mode"    = "direct" | "band"     direct (default): every DP cell of every window is evaluated;
  *                                     band: exact Ukkonen band |i-j| <= k (same counts, ~(2k+1)/m of the work)
+ *   "cell"    = "auto" | "lop3" | "fma3" | "fma"   code of one DP cell in the window-sliced / band kernels:
+ *                 lop3: 5 LOP3 (ALU pipe only); fma3: 4 LOP3 + 3 IMAD; fma: 4 LOP3 + 2 IMAD (FMA pipe takes the
+ *                 subtractions); auto (default) picks per pattern-length class.  Same results, different speed.
+ *   "reduce"  = "auto" | "nccl" | "host"   how the per-GPU count vectors of the one-shot API are combined when
+ *                 "gpus" > 1: one in-place ncclAllReduce per device (NCCL loaded at run time; auto falls back to
+ *                 the host-side sum when libnccl.so.2 is not loadable)
  *   "rblock"  = "1" | "2" | "4" | "auto"     patterns register-blocked per thread (row-parallel kernel)
  *   "tile"    = window starts per CTA tile (multiple of 256) or "auto"   (row-parallel kernel)
  *   "variant" = "0" | "1" | "2"       column-step code variant of the row-parallel kernel

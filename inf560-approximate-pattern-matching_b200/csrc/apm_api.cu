@@ -5,6 +5,7 @@
 #include "../../include/apm_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -62,6 +63,8 @@ struct Options {
     int rblock = 0;  // 0 = auto
     int tile = 0;    // 0 = auto
     int variant = 0; // column-step code variant (see myers_step_fma)
+    int cell = -1;   // DP-cell code of the sliced/band kernels: -1 auto, 0 = 5 LOP3, 1 = 4 LOP3 + 3 IMAD, 2 = 4 LOP3 + 2 IMAD
+    int reduce = 0;  // multi-GPU count reduction: 0 auto (NCCL when loadable), 1 nccl, 2 host sum
     long long dp_scratch_mb = 256;
 };
 std::mutex g_opt_mu;
@@ -137,7 +140,7 @@ struct SlicedList {
     uint2 *d_vscratch = nullptr;  // boundary deltas between column blocks (only when mmax > MC)
     unsigned long long *d_work = nullptr;  // item dispenser of the persistent kernel
     size_t vscratch_bytes = 0;
-    size_t smem_set = 0;
+    size_t smem_set[3] = {0, 0, 0};
 };
 
 template <typename T>
@@ -360,15 +363,15 @@ int launch_myers(apm_plan *pl, Bucket &b, const uint8_t *d_buf, long long buf_le
     return APM_OK;
 }
 
-template <int MC>
+template <int MC, int CELL>
 int launch_sliced_mc(apm_plan *pl, SlicedList &l, SlicedArgs a, long long nwin, cudaStream_t st) {
-    auto fn = sliced_count_kernel<MC>;
+    auto fn = sliced_count_kernel<MC, CELL>;
     const long long ntiles = (nwin + kSlicedTile - 1) / kSlicedTile;
     const int rowsU = sliced_rowsU(l.mmax);
     const size_t smem = sliced_smem_bytes(pl->nplanes, rowsU);
-    if (smem > l.smem_set) {
+    if (smem > l.smem_set[CELL]) {
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        l.smem_set = smem;
+        l.smem_set[CELL] = smem;
     }
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kSlicedThreads, smem));
@@ -409,8 +412,12 @@ int launch_sliced_mc(apm_plan *pl, SlicedList &l, SlicedArgs a, long long nwin, 
 
 // smallest instantiated band half-width >= k
 using BandKernel = void (*)(const SlicedArgs);
-BandKernel pick_band(int k, int *K_out) {
-#define APM_BAND_CASE(KK) if (k <= KK) { *K_out = KK; return band_count_kernel<KK>; }
+BandKernel pick_band(int k, int cell, int *K_out) {
+#define APM_BAND_CASE(KK)                                                                                  \
+    if (k <= KK) {                                                                                         \
+        *K_out = KK;                                                                                       \
+        return cell == 2 ? band_count_kernel<KK, 2> : (cell == 1 ? band_count_kernel<KK, 1> : band_count_kernel<KK, 0>); \
+    }
     APM_BAND_CASE(0) APM_BAND_CASE(1) APM_BAND_CASE(2) APM_BAND_CASE(3) APM_BAND_CASE(4) APM_BAND_CASE(5)
     APM_BAND_CASE(6) APM_BAND_CASE(8) APM_BAND_CASE(10) APM_BAND_CASE(12) APM_BAND_CASE(16)
 #undef APM_BAND_CASE
@@ -420,7 +427,7 @@ BandKernel pick_band(int k, int *K_out) {
 
 int launch_band(apm_plan *pl, SlicedList &l, SlicedArgs a, long long nwin, cudaStream_t st) {
     int K = -1;
-    BandKernel fn = pick_band(pl->k, &K);
+    BandKernel fn = pick_band(pl->k, pl->opt.cell < 0 ? 0 : pl->opt.cell, &K);  // auto: the band rows are issue bound, plain LOP3 wins
     const long long ntiles = (nwin + kSlicedTile - 1) / kSlicedTile;
     const int rowsU = sliced_rowsU(l.mmax + K) + 1;  // the band reaches K columns past the window; +1 lead row
     const int row_cols = 32 + 2 * K;
@@ -474,11 +481,20 @@ int launch_sliced(apm_plan *pl, SlicedList &l, const uint8_t *d_buf, long long b
     a.row_cols = 32;
     a.lead = 0;
     a.work_counter = nullptr;
+    a.c_neg1 = 0xFFFFFFFFu;
     // exact band mode: only the 2K+1 diagonals that can matter for D <= k (worth it when the band is
     // narrower than the matrix)
     if (pl->opt.mode == MODE_BAND && pl->k <= kBandMaxK && 2 * pl->k + 1 < l.mmin)
         return launch_band(pl, l, a, lim - w0, st);
-    return l.MC == 32 ? launch_sliced_mc<32>(pl, l, a, lim - w0, st) : launch_sliced_mc<64>(pl, l, a, lim - w0, st);
+    // auto: measured on B200 (profiles/r01_quick_cell_variants.jsonl) -- the FMA-pipe variants win where the whole
+    // pattern is one register block (m <= 32: 4 LOP3 + 2 IMAD, m <= 64: 4 LOP3 + 3 IMAD); register-file operand
+    // bandwidth, not the pipes, limits the co-issue (tools/ubench/pipe_mix.cu), so the gain is ~6 %
+    const int cell = pl->opt.cell >= 0 ? pl->opt.cell : (l.MC == 32 ? 2 : (l.mmax <= 64 ? 1 : 0));
+    if (cell == 2)
+        return l.MC == 32 ? launch_sliced_mc<32, 2>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 2>(pl, l, a, lim - w0, st);
+    if (cell == 1)
+        return l.MC == 32 ? launch_sliced_mc<32, 1>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 1>(pl, l, a, lim - w0, st);
+    return l.MC == 32 ? launch_sliced_mc<32, 0>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 0>(pl, l, a, lim - w0, st);
 }
 
 int launch_dp(apm_plan *pl, const uint8_t *d_buf, long long buf_offset, long long n_total, long long j_begin,
@@ -629,6 +645,17 @@ int apm_set_option(const char *key, const char *value) {
     } else if (k == "variant") {
         if (v == "0" || v == "1" || v == "2") g_opt.variant = atoi(value);
         else return bad();
+    } else if (k == "cell") {
+        if (v == "auto") g_opt.cell = -1;
+        else if (v == "lop3") g_opt.cell = 0;
+        else if (v == "fma3") g_opt.cell = 1;
+        else if (v == "fma" || v == "fma2") g_opt.cell = 2;
+        else return bad();
+    } else if (k == "reduce") {
+        if (v == "auto") g_opt.reduce = 0;
+        else if (v == "nccl") g_opt.reduce = 1;
+        else if (v == "host") g_opt.reduce = 2;
+        else return bad();
     } else if (k == "dp_scratch_mb") {
         long long mb = atoll(value);
         if (mb < 1 || mb > 65536) return bad();
@@ -651,6 +678,8 @@ const char *apm_get_option(const char *key) {
     else if (k == "rblock") tl_optbuf = o.rblock ? std::to_string(o.rblock) : "auto";
     else if (k == "tile") tl_optbuf = o.tile ? std::to_string(o.tile) : "auto";
     else if (k == "variant") tl_optbuf = std::to_string(o.variant);
+    else if (k == "cell") tl_optbuf = o.cell == 2 ? "fma" : (o.cell == 1 ? "fma3" : (o.cell == 0 ? "lop3" : "auto"));
+    else if (k == "reduce") tl_optbuf = o.reduce == 1 ? "nccl" : (o.reduce == 2 ? "host" : "auto");
     else if (k == "dp_scratch_mb") tl_optbuf = std::to_string(o.dp_scratch_mb);
     else return nullptr;
     return tl_optbuf.c_str();
@@ -880,6 +909,61 @@ int apm_int_peak(int kind, double *ops_per_sec, double *seconds) {
 // ---------------------------------------------------------------------------------------------------
 namespace {
 
+// ---- NCCL, loaded at run time (no link-time dependency): the single-process multi-GPU path sums the
+//      per-GPU count vectors with one in-place ncclAllReduce per device inside a group, over NVLink.
+//      This replaces the MPI_Send/MPI_Recv of per-pattern ints of the reference
+//      (patterns_over_ranks.c:195,389; database_over_ranks.c:179,573).
+struct Nccl {
+    typedef void *comm_t;
+    int (*CommInitAll)(comm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::vector<int> devs;        // devices of the cached communicators
+    std::vector<comm_t> comms;
+};
+std::mutex g_nccl_mu;
+Nccl g_nccl;
+bool g_nccl_tried = false;
+
+bool nccl_load() {
+    if (g_nccl_tried) return g_nccl.ok;
+    g_nccl_tried = true;
+    void *h = nullptr;
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+        h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return false;
+    g_nccl.CommInitAll = (int (*)(Nccl::comm_t *, int, const int *))dlsym(h, "ncclCommInitAll");
+    g_nccl.CommDestroy = (int (*)(Nccl::comm_t))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, Nccl::comm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    g_nccl.ok = g_nccl.CommInitAll && g_nccl.AllReduce && g_nccl.GroupStart && g_nccl.GroupEnd;
+    return g_nccl.ok;
+}
+
+// communicators for exactly this device list (cached across calls; NCCL init costs ~100 ms)
+int nccl_comms_for(const std::vector<int> &devs) {
+    if (g_nccl.devs == devs && !g_nccl.comms.empty()) return APM_OK;
+    if (g_nccl.CommDestroy)
+        for (auto c : g_nccl.comms) g_nccl.CommDestroy(c);
+    g_nccl.comms.assign(devs.size(), nullptr);
+    g_nccl.devs.clear();
+    const int rc = g_nccl.CommInitAll(g_nccl.comms.data(), (int)devs.size(), devs.data());
+    if (rc != 0) {
+        g_nccl.comms.clear();
+        return fail(APM_ECUDA, "ncclCommInitAll: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+    }
+    g_nccl.devs = devs;
+    return APM_OK;
+}
+
 struct DevJob {
     int dev = 0;
     cudaStream_t st = nullptr;
@@ -1002,9 +1086,40 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
                                         (unsigned long long)N, (unsigned long long)j.j0, (unsigned long long)j.j1, j.st)))
             return bail(rc);
     }
+    // ---- combine the per-GPU count vectors
+    bool reduced_on_device = false;
+    if (G > 1 && opt.reduce != 2) {
+        std::lock_guard<std::mutex> lk(g_nccl_mu);
+        if (nccl_load()) {
+            std::vector<int> devs;
+            for (auto &j : jobs) devs.push_back(j.dev);
+            if ((rc = nccl_comms_for(devs))) return bail(rc);
+            int nrc = g_nccl.GroupStart();
+            for (int g = 0; g < G && nrc == 0; ++g) {
+                cudaSetDevice(jobs[g].dev);
+                nrc = g_nccl.AllReduce(jobs[g].plan->d_counts, jobs[g].plan->d_counts, (size_t)nb_patterns, /*ncclUint64*/ 5,
+                                       /*ncclSum*/ 0, g_nccl.comms[g], jobs[g].st);
+            }
+            const int erc = g_nccl.GroupEnd();
+            if (nrc == 0) nrc = erc;
+            if (nrc != 0)
+                return bail(fail(APM_ECUDA, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "error"));
+            reduced_on_device = true;
+        } else if (opt.reduce == 1) {
+            return bail(fail(APM_ECUDA, "reduce=nccl requested but libnccl.so.2 could not be loaded"));
+        }
+    }
     std::vector<long long> part(nb_patterns);
     for (int g = 0; g < G; ++g) {
         cudaSetDevice(jobs[g].dev);
+        if (reduced_on_device) {  // every GPU holds the total; read it once, just drain the others
+            if (g == 0) {
+                if ((rc = apm_plan_read_counts(jobs[0].plan, n_matches, jobs[0].st))) return bail(rc);
+            } else if (cudaStreamSynchronize(jobs[g].st) != cudaSuccess) {
+                return bail(fail(APM_ECUDA, "stream synchronize failed on device %d", jobs[g].dev));
+            }
+            continue;
+        }
         if ((rc = apm_plan_read_counts(jobs[g].plan, part.data(), jobs[g].st))) return bail(rc);
         for (int i = 0; i < nb_patterns; ++i) n_matches[i] += part[i];
     }

@@ -36,7 +36,7 @@ __device__ __forceinline__ const unsigned char *band_row_ptr(const unsigned char
     return plane_row + (c0 >> 5) * row_bytes + (c0 & 31) * 4;
 }
 
-template <int K>
+template <int K, int CELL>
 __global__ void __launch_bounds__(kSlicedThreads, 3) band_count_kernel(const SlicedArgs a) {
     constexpr int BW = 2 * K + 1;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kSlicedThreads, 3) band_count_kernel(const Sli
     const long long nwin = a.w1 - a.w0;
     const long long ntiles = (nwin + kSlicedTile - 1) / kSlicedTile;
     uint32_t phase = 0;
+    const uint32_t neg1 = a.c_neg1;
     const long long nitems = ntiles * a.nsplits;
     const int per_split = (a.npat + a.nsplits - 1) / a.nsplits;
     __shared__ long long s_item;
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(kSlicedThreads, 3) band_count_kernel(const Sli
 #pragma unroll
                 for (int d = 0; d < BW; ++d) {
                     hbp[d] = d > K ? 0xFFFFFFFFu : 0u;
-                    hbm[d] = d > K ? 0u : 0xFFFFFFFFu;
+                    hbm[d] = (d > K && CELL != 2) ? 0u : 0xFFFFFFFFu;  // CELL 2: second plane = [h != 0]
                 }
                 // T[q] = (K - k + number of non-free diagonal steps so far) > q: starting the count at K - k makes
                 // the final test "count > k" the compile-time plane T[K] whatever the runtime k <= K is
@@ -122,15 +123,23 @@ __global__ void __launch_bounds__(kSlicedThreads, 3) band_count_kernel(const Sli
                     for (int d = 0; d < BW; ++d) {
                         const uint32_t q = qc[d];
                         const uint32_t bp = d + 1 < BW ? hbp[d + 1] : 0xFFFFFFFFu;  // above the band: +1
-                        const uint32_t bm = d + 1 < BW ? hbm[d + 1] : 0u;
-                        const uint32_t d0 = lop3<kLutOr3>(q, am, bm);
-                        const uint32_t vm = lop3<kLutAndOr>(bp, q, am);
-                        const uint32_t vp = lop3<kLutOrNor>(bm, d0, bp);
-                        hbp[d] = lop3<kLutOrNor>(am, d0, ap);
-                        hbm[d] = lop3<kLutAndOr>(ap, q, bm);
-                        ap = vp;
-                        am = vm;
-                        if (d == K) z = ~d0;  // main diagonal: the step D[i][i] -> D[i+1][i+1] costs 1
+                        const uint32_t bm = d + 1 < BW ? hbm[d + 1] : cell_plus_second_plane<CELL>();
+                        uint32_t nbp = bp, nbm = bm;
+                        if constexpr (CELL == 0) {  // five LOP3; ~d0 of the main diagonal is the cost of the step
+                            const uint32_t d0 = lop3<kLutOr3>(q, am, bm);
+                            const uint32_t vm = lop3<kLutAndOr>(bp, q, am);
+                            const uint32_t vp = lop3<kLutOrNor>(bm, d0, bp);
+                            nbp = lop3<kLutOrNor>(am, d0, ap);
+                            nbm = lop3<kLutAndOr>(ap, q, bm);
+                            ap = vp;
+                            am = vm;
+                            if (d == K) z = ~d0;
+                        } else {  // FMA-pipe variants of the cell (apm_sliced.cuh); x = ~d0 needs its own LOP3
+                            if (d == K) z = lop3<kLutNor3>(q, am, cell_minus_plane<CELL>(bp, bm));
+                            sliced_cell<CELL>(q, ap, am, nbp, nbm, neg1);
+                        }
+                        hbp[d] = nbp;
+                        hbm[d] = nbm;
                     }
 #pragma unroll
                     for (int q = K; q >= 1; --q) T[q] |= T[q - 1] & z;

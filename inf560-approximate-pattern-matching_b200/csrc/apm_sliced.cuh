@@ -74,6 +74,7 @@ struct SlicedArgs {
     int row_cols;                // 32-bit windows stored per U row (32; 32 + 2K for the band kernel)
     int lead;                    // text positions staged BEFORE the tile start (0; 32 for the band kernel)
     unsigned long long *work_counter;  // zeroed before the launch: dynamic (tile, range) item dispenser
+    uint32_t c_neg1;             // the constant 0xFFFFFFFF, opaque to ptxas (multiplier of the FMA-pipe subtractions)
 };
 
 // one LOP3: any boolean function of three words, LUT evaluated on a = 0xF0, b = 0xCC, c = 0xAA.
@@ -88,6 +89,22 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
 constexpr int kLutOr3 = 0xFE;        // a | b | c
 constexpr int kLutAndOr = 0xE0;      // a & (b | c)
 constexpr int kLutOrNor = 0xF1;      // a | ~(b | c)
+constexpr int kLutNor3 = 0x01;       // ~(a | b | c)
+constexpr int kLutOrAndN = 0xF4;     // a | (b & ~c)
+constexpr int kLutXor3 = 0x96;       // a ^ b ^ c
+constexpr int kLutAndOrN = 0xD0;     // a & (b | ~c)
+
+// c - a on the FMA pipe: IMAD with the multiplier -1 held where ptxas cannot see its value (otherwise the
+// subtraction becomes an IADD3 and goes back to the ALU pipe, the one the LOP3s saturate)
+__device__ __forceinline__ uint32_t fma_sub(uint32_t c, uint32_t a, uint32_t neg1) {
+    uint32_t d;
+#ifdef APM_FMA_SUB_PLAIN
+    asm("sub.u32 %0, %1, %2;" : "=r"(d) : "r"(c), "r"(a));
+#else
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(neg1), "r"(c));
+#endif
+    return d;
+}
 
 // full adder on bit-planes: a <- a ^ b ^ c, returns majority(a, b, c)   (2 LOP3)
 __device__ __forceinline__ uint32_t plane_fa(uint32_t &a, uint32_t b, uint32_t c) {
@@ -125,19 +142,67 @@ struct SumPlanes {  // adds the planes of columns 2I and 2I+1 (h+ and ~h- of eac
 
 // One DP cell for 32 windows.  (ap, am) = vertical delta coming from the left neighbour, (bp, bm) =
 // horizontal delta coming from the row above; both are replaced by the deltas of this cell.
-__device__ __forceinline__ void sliced_cell(uint32_t q, uint32_t &ap, uint32_t &am, uint32_t &bp, uint32_t &bm) {
-    // a+ & a- = 0 and b+ & b- = 0, so b+ & d0 = b+ & (eq | a-): the chain a- -> a-' that links a cell to
-    // its right neighbour is a single LOP3 deep
-    const uint32_t d0 = lop3<kLutOr3>(q, am, bm);
-    const uint32_t vm = lop3<kLutAndOr>(bp, q, am);
-    const uint32_t vp = lop3<kLutOrNor>(bm, d0, bp);
-    const uint32_t hp2 = lop3<kLutOrNor>(am, d0, ap);
-    const uint32_t hm2 = lop3<kLutAndOr>(ap, q, bm);
-    bp = hp2;
-    bm = hm2;
-    ap = vp;
-    am = vm;
+//   CELL 0: five LOP3 (all on the ALU pipe).
+//   CELL 1: four LOP3 + three IMAD.  With x = ~d0 (the diagonal step D[i][j] - D[i-1][j-1], one bit) the deltas
+//           obey h = x - a as integers PER BIT POSITION: h+ - h- = x - a+ + a-.  Every term is 0/1 and so is
+//           h+, hence the identity also holds for the whole 32-bit words modulo 2^32 (borrows of intermediate
+//           results cancel), and h+ = a- - ((a+ - x) - h-) can be evaluated by three subtractions on the
+//           otherwise idle FMA pipe.  The ALU pipe, which bounds the kernel, executes 4 instead of 5
+//           instructions per cell; h+ is only consumed one row later, so the longer latency is free.
+template <int CELL>
+__device__ __forceinline__ void sliced_cell(uint32_t q, uint32_t &ap, uint32_t &am, uint32_t &bp, uint32_t &bm,
+                                            uint32_t neg1) {
+    if constexpr (CELL == 0) {
+        // a+ & a- = 0 and b+ & b- = 0, so b+ & d0 = b+ & (eq | a-): the chain a- -> a-' that links a cell to
+        // its right neighbour is a single LOP3 deep
+        const uint32_t d0 = lop3<kLutOr3>(q, am, bm);
+        const uint32_t vm = lop3<kLutAndOr>(bp, q, am);
+        const uint32_t vp = lop3<kLutOrNor>(bm, d0, bp);
+        const uint32_t hp2 = lop3<kLutOrNor>(am, d0, ap);
+        const uint32_t hm2 = lop3<kLutAndOr>(ap, q, bm);
+        bp = hp2;
+        bm = hm2;
+        ap = vp;
+        am = vm;
+    } else if constexpr (CELL == 1) {
+        const uint32_t x = lop3<kLutNor3>(q, am, bm);
+        const uint32_t vm = lop3<kLutAndOr>(bp, q, am);
+        const uint32_t vp = lop3<kLutOrAndN>(bm, x, bp);
+        const uint32_t hm2 = lop3<kLutAndOr>(ap, q, bm);
+        const uint32_t t1 = fma_sub(ap, x, neg1);     // a+ - x
+        const uint32_t t2 = fma_sub(t1, hm2, neg1);   // a+ - x - h-
+        bp = fma_sub(am, t2, neg1);                   // h+ = a- - a+ + x + h-
+        bm = hm2;
+        ap = vp;
+        am = vm;
+    } else {
+        // CELL 2: four LOP3 + two IMAD, on a different encoding of the deltas:
+        //   vertical   a: am = [a == -1], ap = [a != 0]        horizontal b: bp = [b == +1], bm = [b != 0]
+        // v- needs only (b+, eq, a-), as before.  [v != 0] = s - u with s = [b != 0] | ~(eq | a-) (one LOP3) and
+        // u = b+ & x = b+ - v- (x = ~(eq | a- | b-) is the diagonal step; bitwise exact, no borrows).  The
+        // deltas obey v - h = a - b, so the parities agree: [h != 0] = [a != 0] ^ [b != 0] ^ [v != 0] (one
+        // LOP3), and h+ = [h != 0] & ~[a == +1].  The row recurrence still runs through v- alone (one LOP3 deep);
+        // everything behind the two subtractions is only consumed a cell / a row later.
+        const uint32_t vm = lop3<kLutAndOr>(bp, q, am);
+        const uint32_t s = lop3<kLutOrNor>(bm, q, am);
+        const uint32_t u = fma_sub(bp, vm, neg1);
+        const uint32_t vnz = fma_sub(s, u, neg1);
+        const uint32_t hnz = lop3<kLutXor3>(ap, bm, vnz);
+        bp = lop3<kLutAndOrN>(hnz, am, ap);
+        bm = hnz;
+        ap = vnz;
+        am = vm;
+    }
 }
+
+// second plane of a horizontal delta of +1 (the DP boundary D[0][j] - D[0][j-1], and the neutral value of
+// unused columns): h- = 0 for CELL 0/1, [h != 0] = 1 for CELL 2.  The first plane (h+) is all ones, and the
+// vertical boundary delta +1 is (ap, am) = (all ones, 0) in every encoding.
+template <int CELL>
+__device__ __forceinline__ constexpr uint32_t cell_plus_second_plane() { return CELL == 2 ? 0xFFFFFFFFu : 0u; }
+// h- plane from the state planes
+template <int CELL>
+__device__ __forceinline__ uint32_t cell_minus_plane(uint32_t bp, uint32_t bm) { return CELL == 2 ? (bm & ~bp) : bm; }
 
 // Row-major sweep of one column block (MC columns starting at the column the pointer `urow` is positioned
 // on) over all `rows` pattern symbols.  urow = this thread's row origin inside plane 0 of the U table,
@@ -147,10 +212,11 @@ __device__ __forceinline__ void sliced_cell(uint32_t q, uint32_t &ap, uint32_t &
 // without VIN the left edge is the DP boundary D[i][0] = i (+1).
 // FULL (all MC columns used): branch-free and software pipelined -- the match words of the next column
 // group (same row, or the first group of the next row) are requested before the current group is computed.
-template <int MC, bool FULL, bool VIN, bool VOUT>
+template <int MC, int CELL, bool FULL, bool VIN, bool VOUT>
 __device__ __forceinline__ void sliced_sweep(const unsigned char *__restrict__ urow, const uint8_t *__restrict__ pc,
                                              int rows, int width, uint32_t plane_bytes, uint32_t (&hp)[MC],
-                                             uint32_t (&hm)[MC], uint2 *__restrict__ vs, long long vstride) {
+                                             uint32_t (&hm)[MC], uint2 *__restrict__ vs, long long vstride,
+                                             uint32_t neg1) {
     uint32_t code_next = __ldg(pc + 1);
     uint2 vin = make_uint2(0xFFFFFFFFu, 0u);
     if constexpr (VIN) vin = vs[0];
@@ -182,7 +248,7 @@ __device__ __forceinline__ void sliced_sweep(const unsigned char *__restrict__ u
                 }
 #pragma unroll
                 for (int cc = 0; cc < G; ++cc)
-                    sliced_cell((cc & 1) ? cur[cc >> 1].y : cur[cc >> 1].x, ap, am, hp[gi * G + cc], hm[gi * G + cc]);
+                    sliced_cell<CELL>((cc & 1) ? cur[cc >> 1].y : cur[cc >> 1].x, ap, am, hp[gi * G + cc], hm[gi * G + cc], neg1);
             }
             if constexpr (VOUT) vs[(long long)i * vstride] = make_uint2(ap, am);
             e = e_next;
@@ -198,14 +264,14 @@ __device__ __forceinline__ void sliced_sweep(const unsigned char *__restrict__ u
             for (int c = 0; c < MC; c += 2) {
                 if ((c % CH) == 0 && c >= width) break;  // uniform: the same for the whole CTA
                 const uint2 eq = *reinterpret_cast<const uint2 *>(e + (c >> 5) * kURowBytes + (c & 31) * 4);
-                sliced_cell(eq.x, ap, am, hp[c], hm[c]);
-                sliced_cell(eq.y, ap, am, hp[c + 1], hm[c + 1]);
+                sliced_cell<CELL>(eq.x, ap, am, hp[c], hm[c], neg1);
+                sliced_cell<CELL>(eq.y, ap, am, hp[c + 1], hm[c + 1], neg1);
             }
             if constexpr (VOUT) vs[(long long)i * vstride] = make_uint2(ap, am);
         }
 #pragma unroll
         for (int j = 0; j < MC; ++j)  // columns >= width: back to the neutral boundary value (they add a constant)
-            if (j >= width) { hp[j] = 0xFFFFFFFFu; hm[j] = 0u; }
+            if (j >= width) { hp[j] = 0xFFFFFFFFu; hm[j] = cell_plus_second_plane<CELL>(); }
     }
 }
 
@@ -281,7 +347,7 @@ __device__ __forceinline__ TileGeom sliced_stage_tile(const SlicedArgs &a, long 
 // (uniform addresses, L1 broadcast).  MC = columns per register block: 32 (patterns m <= 32, one block)
 // or 64 (any m <= kSlicedMaxLen, ceil(m/64) blocks chained through the global boundary scratch).
 // ------------------------------------------------------------------------------------------------
-template <int MC>
+template <int MC, int CELL>
 __global__ void __launch_bounds__(kSlicedThreads, MC == 64 ? 3 : 4) sliced_count_kernel(const SlicedArgs a) {
     static_assert(MC == 32 || MC == 64, "MC must be 32 or 64");
     constexpr int LOG = MC == 32 ? 6 : 7;  // 2*MC planes are summed per block: value range [0, 2*MC]
@@ -307,6 +373,7 @@ __global__ void __launch_bounds__(kSlicedThreads, MC == 64 ? 3 : 4) sliced_count
     const long long vstride = (long long)gridDim.x * kSlicedThreads;
     uint2 *vs = a.vscratch + ((long long)blockIdx.x * kSlicedThreads + tid);
     uint32_t phase = 0;
+    const uint32_t neg1 = a.c_neg1;
 
     const long long nitems = ntiles * a.nsplits;
     const int per_split = (a.npat + a.nsplits - 1) / a.nsplits;
@@ -345,22 +412,26 @@ __global__ void __launch_bounds__(kSlicedThreads, MC == 64 ? 3 : 4) sliced_count
                     const unsigned char *ub = urow + (size_t)b * (MC / 32) * kURowBytes;  // MC columns = MC/32 U rows
                     uint32_t hp[MC], hm[MC];
 #pragma unroll
-                    for (int j = 0; j < MC; ++j) { hp[j] = 0xFFFFFFFFu; hm[j] = 0u; }  // D[0][j] - D[0][j-1] = +1
+                    for (int j = 0; j < MC; ++j) { hp[j] = 0xFFFFFFFFu; hm[j] = cell_plus_second_plane<CELL>(); }  // D[0][j] - D[0][j-1] = +1
                     if (MC == 32 || nblk == 1) {
-                        if (width == MC) sliced_sweep<MC, true, false, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride);
-                        else sliced_sweep<MC, false, false, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride);
+                        if (width == MC) sliced_sweep<MC, CELL, true, false, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
+                        else sliced_sweep<MC, CELL, false, false, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
                     } else if (b == 0) {
-                        sliced_sweep<MC, true, false, true>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride);
+                        sliced_sweep<MC, CELL, true, false, true>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
                     } else if (b < nblk - 1) {
-                        sliced_sweep<MC, true, true, true>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride);
+                        sliced_sweep<MC, CELL, true, true, true>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
                     } else {
-                        if (width == MC) sliced_sweep<MC, true, true, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride);
-                        else sliced_sweep<MC, false, true, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride);
+                        if (width == MC) sliced_sweep<MC, CELL, true, true, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
+                        else sliced_sweep<MC, CELL, false, true, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
                     }
                     // block sum: sum_j (h+[j] + ~h-[j]) over the MC columns of the last row (unused ones add 2)
                     uint32_t acc[NL], pend[NL];
 #pragma unroll
                     for (int l = 0; l < NL; ++l) { acc[l] = 0u; pend[l] = 0u; }
+                    if constexpr (CELL == 2) {
+#pragma unroll
+                        for (int j = 0; j < MC; ++j) hm[j] = cell_minus_plane<CELL>(hp[j], hm[j]);
+                    }
                     SumPlanes<MC, 0, NL>::run(hp, hm, acc, pend);
                     acc[LOG] = pend[LOG];
                     planes_add<NL>(tot, acc);

@@ -20,7 +20,7 @@ CASES = cases()
 @pytest.fixture(autouse=True)
 def _default_options():
     for k, v in (("kernel", "auto"), ("rblock", "auto"), ("tile", "auto"), ("gpus", "1"), ("shard", "auto"),
-                 ("variant", "0"), ("mode", "direct")):
+                 ("variant", "0"), ("mode", "direct"), ("cell", "auto"), ("reduce", "auto")):
         apm_b200.set_option(k, v)
     yield
 
@@ -42,6 +42,46 @@ def test_golden_host_api(case, kernel):
     got = apm_b200.count_matches(FX[case["text"]], case["patterns"], case["k"])
     assert got == case["expected"]
     assert apm_b200.launch_count() > before, "no CUDA kernel launched"
+
+
+@pytest.mark.parametrize("mode", ["direct", "band"])
+@pytest.mark.parametrize("cell", ["auto", "lop3", "fma3", "fma"])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c["name"])
+def test_golden_both_cell_codes(case, cell, mode):
+    """The DP cell as 5 LOP3 (lop3), 4 LOP3 + 3 FMA-pipe subtractions (fma3), 4 LOP3 + 2 subtractions on the
+    (minus, nonzero) / (plus, nonzero) delta encoding (fma); auto picks per pattern-length class."""
+    apm_b200.set_option("kernel", "sliced")
+    apm_b200.set_option("cell", cell)
+    apm_b200.set_option("mode", mode)
+    assert apm_b200.get_option("cell") == cell
+    assert apm_b200.count_matches(FX[case["text"]], case["patterns"], case["k"]) == case["expected"]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_cell_codes_agree_on_random_slabs(seed):
+    """all DP-cell codes on 2 MB of random text, mixed lengths (1..300), direct and band mode."""
+    rng = np.random.default_rng(4000 + seed)
+    n = 2_000_000
+    text = oracle.synth_text(0x5EED0001, 1000 * seed, n).tobytes()
+    pats = []
+    for m in (1, 7, 31, 32, 33, 50, 64, 65, 100, 128, 200, 300):
+        off = int(rng.integers(0, n - m))
+        p = bytearray(text[off:off + m])
+        for s in range(int(rng.integers(0, 6))):
+            pos = int(rng.integers(0, m))
+            p[pos] = ord("ACGT"[int(rng.integers(0, 4))])
+        pats.append(bytes(p))
+    k = int(rng.integers(0, 7))
+    out = {}
+    for mode in ("direct", "band"):
+        for cell in ("lop3", "fma3", "fma"):
+            apm_b200.set_option("mode", mode)
+            apm_b200.set_option("cell", cell)
+            out[(mode, cell)] = apm_b200.count_matches(text, pats, k)
+    ref = out[("direct", "lop3")]
+    assert sum(ref) > 0
+    for key, v in out.items():
+        assert v == ref, key
 
 
 @pytest.mark.parametrize("name", ["config1_readme", "easy_k2", "small_k25", "small_m200_k10", "config2"])
@@ -479,6 +519,8 @@ def test_one_shot_api_two_gpus_single_process():
     apm_b200.set_option("gpus", "1")
     want = apm_b200.count_matches(text, pats, k)
     apm_b200.set_option("gpus", "2")
-    for shard in ("db", "patterns", "auto"):
-        apm_b200.set_option("shard", shard)
-        assert apm_b200.count_matches(text, pats, k) == want, shard
+    for reduce in ("auto", "nccl", "host"):  # NCCL all-reduce of the count vectors over NVLink / host-side sum
+        apm_b200.set_option("reduce", reduce)
+        for shard in ("db", "patterns", "auto"):
+            apm_b200.set_option("shard", shard)
+            assert apm_b200.count_matches(text, pats, k) == want, (reduce, shard)

@@ -33,13 +33,15 @@ def main():
     torch.cuda.synchronize()
     st = torch.cuda.current_stream().cuda_stream
     combos = []
-    for mode in ("band", "direct"):
-        combos.append((64, 4, 256, "4", "512", 16 << 20, "0", "auto", mode))
-        combos.append((200, 10, 64, "1", "512", 4 << 20, "0", "auto", mode))
-        combos.append((32, 2, 256, "4", "512", 32 << 20, "0", "auto", mode))
-        combos.append((64, 8, 256, "4", "512", 16 << 20, "0", "auto", mode))
-        combos.append((1000, 16, 16, "1", "512", 2 << 20, "0", "auto", mode))
-    for m, k, P, rb, tile, slab, var, kern, mode in combos:
+    for mode in ("direct", "band"):
+      for cell in ("lop3", "fma3", "fma"):
+        combos.append((64, 4, 256, "4", "512", 16 << 20, "0", "auto", mode, cell))
+        combos.append((200, 10, 64, "1", "512", 4 << 20, "0", "auto", mode, cell))
+        combos.append((32, 2, 256, "4", "512", 32 << 20, "0", "auto", mode, cell))
+        combos.append((50, 0, 256, "4", "512", 16 << 20, "0", "auto", mode, cell))
+        combos.append((1000, 16, 16, "1", "512", 2 << 20, "0", "auto", mode, cell))
+    for m, k, P, rb, tile, slab, var, kern, mode, cell in combos:
+        apm_b200.set_option("cell", cell)
         apm_b200.set_option("rblock", rb)
         apm_b200.set_option("tile", tile)
         apm_b200.set_option("variant", var)
@@ -64,7 +66,7 @@ def main():
             nw = (m + 31) // 32
             cells = slab * P * m * m
             ops = slab * P * m * nw * 10
-            print(json.dumps({"m": m, "k": k, "P": P, "kernel": kern, "mode": mode, "rblock": rb, "tile": tile, "variant": var, "slab": slab, "ms": ms,
+            print(json.dumps({"m": m, "k": k, "P": P, "kernel": kern, "mode": mode, "cell": cell, "rblock": rb, "tile": tile, "variant": var, "slab": slab, "ms": ms,
                               "GCUPS": cells / ms / 1e6, "Tiops": ops / ms / 1e9,
                               "frac_of_lop3_iadd3_peak": ops / (ms * 1e-3) / peaks["lop3+iadd3"]}), flush=True)
 
