@@ -75,6 +75,7 @@ int apm_count_matches_file(const char *path, const char *const *patterns, const 
  *   "reduce"  = "auto" | "nccl" | "host"   how the per-GPU count vectors of the one-shot API are combined when
  *                 "gpus" > 1: one in-place ncclAllReduce per device (NCCL loaded at run time; auto falls back to
  *                 the host-side sum when libnccl.so.2 is not loadable)
+ *   "cache_mb" = device memory (MiB) kept cached between calls instead of cudaFree'd (default 4096)
  *   "rblock"  = "1" | "2" | "4" | "auto"     patterns register-blocked per thread (row-parallel kernel)
  *   "tile"    = window starts per CTA tile (multiple of 256) or "auto"   (row-parallel kernel)
  *   "variant" = "0" | "1" | "2"       column-step code variant of the row-parallel kernel
@@ -135,6 +136,10 @@ int apm_int_peak(int kind, double *ops_per_sec, double *seconds);
 
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches).    */
 unsigned long long apm_launch_count(void);
+
+/* Returns the device memory (and the pinned file-staging buffers) the library keeps cached between calls to
+ * the driver.  Option "cache_mb" bounds the cache (default 4096; 0 = keep nothing).                  */
+int apm_release_cache(void);
 
 const char *apm_version(void);
 

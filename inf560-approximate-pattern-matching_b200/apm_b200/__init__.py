@@ -27,7 +27,7 @@ EXPORTS = [
     "apm_device_count", "apm_set_device", "apm_plan_create", "apm_plan_destroy", "apm_plan_count_device",
     "apm_plan_set_pattern_shard", "apm_plan_zero_counts", "apm_plan_counts_device_ptr",
     "apm_plan_read_counts", "apm_plan_max_pattern_len", "apm_synth_text_device", "apm_int_peak",
-    "apm_launch_count", "apm_version",
+    "apm_launch_count", "apm_version", "apm_release_cache",
 ]
 
 
@@ -80,16 +80,27 @@ def _check(rc: int) -> None:
 
 
 def _pattern_arrays(patterns: Sequence[bytes]):
+    """char*[] / int[] views of the patterns: ONE flat host buffer + pointers into it (4096 patterns: ~1 ms)."""
     pats = [bytes(p) for p in patterns]
     n = len(pats)
-    bufs = [C.create_string_buffer(p, len(p)) if len(p) else C.create_string_buffer(1) for p in pats]
-    ptrs = (C.c_void_p * max(n, 1))(*[C.addressof(b) for b in bufs])
+    flat = C.create_string_buffer(b"".join(pats) + b"\0")
+    base = C.addressof(flat)
+    addrs, pos = [], 0
+    for p in pats:
+        addrs.append(base + pos)
+        pos += len(p)
+    ptrs = (C.c_void_p * max(n, 1))(*addrs)
     lens = (C.c_int * max(n, 1))(*[len(p) for p in pats])
-    return bufs, ptrs, lens, n
+    return flat, ptrs, lens, n
 
 
 def set_option(key: str, value) -> None:
     _check(lib().apm_set_option(key.encode(), str(value).encode()))
+
+
+def release_cache() -> None:
+    """Hand the device memory the library caches between calls back to the driver."""
+    _check(lib().apm_release_cache())
 
 
 def get_option(key: str) -> str | None:

@@ -5,6 +5,8 @@
 #include "../../include/apm_b200.h"
 
 #include <cuda_runtime.h>
+#include <chrono>
+#include <map>
 #include <dlfcn.h>
 #include <fcntl.h>
 #include <sys/stat.h>
@@ -66,6 +68,7 @@ struct Options {
     int cell = -1;   // DP-cell code of the sliced/band kernels: -1 auto, 0 = 5 LOP3, 1 = 4 LOP3 + 3 IMAD, 2 = 4 LOP3 + 2 IMAD
     int reduce = 0;  // multi-GPU count reduction: 0 auto (NCCL when loadable), 1 nccl, 2 host sum
     long long dp_scratch_mb = 256;
+    long long cache_mb = 4096;  // device memory kept for reuse between calls (dev_alloc / dev_free)
 };
 std::mutex g_opt_mu;
 Options g_opt;
@@ -86,6 +89,88 @@ int device_ready(int *ndev) {
     }
     *ndev = n;
     return APM_OK;
+}
+
+
+// ---- device-memory cache -----------------------------------------------------------------------------
+// cudaMalloc / cudaFree cost 0.1 - 100 ms each and cudaFree synchronises the device; the one-shot API would
+// pay ~15 of them per call (measured with APM_TRACE=1: up to 126 ms in "release").  Freed blocks are kept per
+// device in size classes and handed out again; everything cached can be returned to the driver with
+// apm_release_cache().  Callers only free a block after the work using it has been synchronised.
+struct DevPool {
+    std::mutex mu;
+    std::map<std::pair<int, size_t>, std::vector<void *>> free_blocks;  // (device, class bytes) -> blocks
+    std::map<void *, std::pair<int, size_t>> live;                      // block -> (device, class bytes)
+    size_t cached_bytes = 0;
+    uint8_t *pinned[2] = {nullptr, nullptr};                            // file-ingest staging buffers
+};
+DevPool g_pool;
+constexpr size_t kPinnedChunk = (size_t)32 << 20;
+
+size_t pool_class(size_t bytes) {
+    size_t c = 512;
+    if (bytes > ((size_t)1 << 20)) return (bytes + ((size_t)2 << 20) - 1) / ((size_t)2 << 20) * ((size_t)2 << 20);
+    while (c < bytes) c <<= 1;
+    return c;
+}
+
+cudaError_t dev_alloc(void **p, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const size_t cls = pool_class(std::max<size_t>(bytes, 1));
+    {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        auto it = g_pool.free_blocks.find({dev, cls});
+        if (it != g_pool.free_blocks.end() && !it->second.empty()) {
+            *p = it->second.back();
+            it->second.pop_back();
+            g_pool.cached_bytes -= cls;
+            g_pool.live[*p] = {dev, cls};
+            return cudaSuccess;
+        }
+    }
+    e = cudaMalloc(p, cls);
+    if (e != cudaSuccess) {  // give the cache back to the driver and retry once
+        cudaGetLastError();
+        apm_release_cache();
+        e = cudaMalloc(p, cls);
+    }
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        g_pool.live[*p] = {dev, cls};
+    }
+    return e;
+}
+template <typename T>
+cudaError_t dev_alloc_t(T **p, size_t bytes) { return dev_alloc((void **)p, bytes); }
+
+void dev_free(void *p) {
+    if (!p) return;
+    size_t limit;
+    {
+        std::lock_guard<std::mutex> lk(g_opt_mu);
+        limit = (size_t)g_opt.cache_mb << 20;
+    }
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    auto it = g_pool.live.find(p);
+    if (it == g_pool.live.end()) {  // not ours (cannot happen) -- hand it to the driver
+        cudaFree(p);
+        return;
+    }
+    const int dev = it->second.first;
+    const size_t cls = it->second.second;
+    g_pool.live.erase(it);
+    if (g_pool.cached_bytes + cls > limit) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != dev) cudaSetDevice(dev);
+        cudaFree(p);
+        if (cur != dev) cudaSetDevice(cur);
+        return;
+    }
+    g_pool.free_blocks[{dev, cls}].push_back(p);
+    g_pool.cached_bytes += cls;
 }
 
 // ---- kernel dispatch table ------------------------------------------------------------------------
@@ -147,7 +232,7 @@ template <typename T>
 int upload(T **dptr, const std::vector<T> &h) {
     *dptr = nullptr;
     if (h.empty()) return APM_OK;
-    CUDA_TRY(cudaMalloc((void **)dptr, h.size() * sizeof(T)));
+    CUDA_TRY(dev_alloc((void **)dptr, h.size() * sizeof(T)));
     CUDA_TRY(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
     return APM_OK;
 }
@@ -178,21 +263,21 @@ namespace {
 
 void free_work(apm_plan *pl) {
     for (auto &b : pl->buckets) {
-        cudaFree(b.d_peq);
-        cudaFree(b.d_group_m);
-        cudaFree(b.d_group_pat);
+        dev_free(b.d_peq);
+        dev_free(b.d_group_m);
+        dev_free(b.d_group_pat);
     }
     pl->buckets.clear();
     for (auto &l : pl->sliced) {
-        cudaFree(l.d_codes);
-        cudaFree(l.d_m);
-        cudaFree(l.d_id);
-        cudaFree(l.d_vscratch);
-        cudaFree(l.d_work);
+        dev_free(l.d_codes);
+        dev_free(l.d_m);
+        dev_free(l.d_id);
+        dev_free(l.d_vscratch);
+        dev_free(l.d_work);
     }
     pl->sliced.clear();
-    cudaFree(pl->d_tail_list);
-    cudaFree(pl->d_all_list);
+    dev_free(pl->d_tail_list);
+    dev_free(pl->d_all_list);
     pl->d_tail_list = pl->d_all_list = nullptr;
     pl->tail_list.clear();
     pl->all_list.clear();
@@ -298,11 +383,11 @@ int ensure_scratch(apm_plan *pl, size_t bytes) {
     if (bytes <= pl->scratch_bytes) return APM_OK;
     if (pl->d_scratch) {
         CUDA_TRY(cudaDeviceSynchronize());
-        CUDA_TRY(cudaFree(pl->d_scratch));
+        dev_free(pl->d_scratch);
         pl->d_scratch = nullptr;
         pl->scratch_bytes = 0;
     }
-    CUDA_TRY(cudaMalloc((void **)&pl->d_scratch, bytes));
+    CUDA_TRY(dev_alloc((void **)&pl->d_scratch, bytes));
     pl->scratch_bytes = bytes;
     return APM_OK;
 }
@@ -388,15 +473,15 @@ int launch_sliced_mc(apm_plan *pl, SlicedList &l, SlicedArgs a, long long nwin, 
         if (need > l.vscratch_bytes) {
             if (l.d_vscratch) {
                 CUDA_TRY(cudaDeviceSynchronize());
-                CUDA_TRY(cudaFree(l.d_vscratch));
+                dev_free(l.d_vscratch);
                 l.d_vscratch = nullptr;
                 l.vscratch_bytes = 0;
             }
-            CUDA_TRY(cudaMalloc((void **)&l.d_vscratch, need));
+            CUDA_TRY(dev_alloc((void **)&l.d_vscratch, need));
             l.vscratch_bytes = need;
         }
     }
-    if (!l.d_work) CUDA_TRY(cudaMalloc((void **)&l.d_work, sizeof(unsigned long long)));
+    if (!l.d_work) CUDA_TRY(dev_alloc((void **)&l.d_work, sizeof(unsigned long long)));
     CUDA_TRY(cudaMemsetAsync(l.d_work, 0, sizeof(unsigned long long), st));
     a.work_counter = l.d_work;
     a.vscratch = l.d_vscratch;
@@ -441,7 +526,7 @@ int launch_band(apm_plan *pl, SlicedList &l, SlicedArgs a, long long nwin, cudaS
     const long long max_splits = std::max<long long>(1, l.npat / 32);
     const long long nsplits = std::max<long long>(1, std::min<long long>(max_splits, (64 * capacity + ntiles - 1) / ntiles));
     const unsigned gx = (unsigned)std::min<long long>(ntiles * nsplits, capacity);
-    if (!l.d_work) CUDA_TRY(cudaMalloc((void **)&l.d_work, sizeof(unsigned long long)));
+    if (!l.d_work) CUDA_TRY(dev_alloc((void **)&l.d_work, sizeof(unsigned long long)));
     CUDA_TRY(cudaMemsetAsync(l.d_work, 0, sizeof(unsigned long long), st));
     a.work_counter = l.d_work;
     a.nsplits = (int)nsplits;
@@ -584,6 +669,26 @@ int check_patterns(const char *const *patterns, const int *pattern_len, int nb_p
 extern "C" {
 
 const char *apm_last_error(void) { return tl_err.c_str(); }
+int apm_release_cache(void) {
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto &kv : g_pool.free_blocks) {
+        if (kv.second.empty()) continue;
+        cudaSetDevice(kv.first.first);
+        for (void *p : kv.second) cudaFree(p);
+        kv.second.clear();
+    }
+    g_pool.free_blocks.clear();
+    g_pool.cached_bytes = 0;
+    for (int i = 0; i < 2; ++i) {
+        if (g_pool.pinned[i]) cudaFreeHost(g_pool.pinned[i]);
+        g_pool.pinned[i] = nullptr;
+    }
+    cudaSetDevice(cur);
+    return APM_OK;
+}
+
 const char *apm_version(void) { return "apm_b200 0.1 (sm_100a)"; }
 unsigned long long apm_launch_count(void) { return g_launches.load(); }
 
@@ -656,6 +761,10 @@ int apm_set_option(const char *key, const char *value) {
         else if (v == "nccl") g_opt.reduce = 1;
         else if (v == "host") g_opt.reduce = 2;
         else return bad();
+    } else if (k == "cache_mb") {
+        long long mb = atoll(value);
+        if (v.empty() || v.find_first_not_of("0123456789") != std::string::npos || mb > (1ll << 20)) return bad();
+        g_opt.cache_mb = mb;
     } else if (k == "dp_scratch_mb") {
         long long mb = atoll(value);
         if (mb < 1 || mb > 65536) return bad();
@@ -680,6 +789,7 @@ const char *apm_get_option(const char *key) {
     else if (k == "variant") tl_optbuf = std::to_string(o.variant);
     else if (k == "cell") tl_optbuf = o.cell == 2 ? "fma" : (o.cell == 1 ? "fma3" : (o.cell == 0 ? "lop3" : "auto"));
     else if (k == "reduce") tl_optbuf = o.reduce == 1 ? "nccl" : (o.reduce == 2 ? "host" : "auto");
+    else if (k == "cache_mb") tl_optbuf = std::to_string(o.cache_mb);
     else if (k == "dp_scratch_mb") tl_optbuf = std::to_string(o.dp_scratch_mb);
     else return nullptr;
     return tl_optbuf.c_str();
@@ -742,7 +852,7 @@ int apm_plan_create(const char *const *patterns, const int *pattern_len, int nb_
     if ((rc = upload(&pl->d_pat_bytes, flat))) return cleanup_fail(rc);
     if ((rc = upload(&pl->d_pat_off, off))) return cleanup_fail(rc);
     if ((rc = upload(&pl->d_pat_len, len))) return cleanup_fail(rc);
-    e = cudaMalloc((void **)&pl->d_counts, sizeof(unsigned long long) * std::max(1, nb_patterns));
+    e = dev_alloc((void **)&pl->d_counts, sizeof(unsigned long long) * std::max(1, nb_patterns));
     if (e == cudaSuccess) e = cudaMemset(pl->d_counts, 0, sizeof(unsigned long long) * std::max(1, nb_patterns));
     if (e != cudaSuccess) {
         fail(APM_ECUDA, "allocating counters: %s", cudaGetErrorString(e));
@@ -758,14 +868,15 @@ int apm_plan_destroy(apm_plan *pl) {
     int cur = 0;
     cudaGetDevice(&cur);
     cudaSetDevice(pl->device);
+    cudaDeviceSynchronize();  // the blocks go back to the cache: nothing in flight may still use them
     free_work(pl);
-    cudaFree(pl->d_code_of);
-    cudaFree(pl->d_plane_of);
-    cudaFree(pl->d_pat_bytes);
-    cudaFree(pl->d_pat_off);
-    cudaFree(pl->d_pat_len);
-    cudaFree(pl->d_counts);
-    cudaFree(pl->d_scratch);
+    dev_free(pl->d_code_of);
+    dev_free(pl->d_plane_of);
+    dev_free(pl->d_pat_bytes);
+    dev_free(pl->d_pat_off);
+    dev_free(pl->d_pat_len);
+    dev_free(pl->d_counts);
+    dev_free(pl->d_scratch);
     cudaSetDevice(cur);
     delete pl;
     return APM_OK;
@@ -871,7 +982,7 @@ int apm_int_peak(int kind, double *ops_per_sec, double *seconds) {
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     uint32_t *d_out = nullptr;
-    CUDA_TRY(cudaMalloc((void **)&d_out, 64));
+    CUDA_TRY(dev_alloc((void **)&d_out, 64));
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
@@ -897,7 +1008,7 @@ int apm_int_peak(int kind, double *ops_per_sec, double *seconds) {
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFree(d_out);
+    dev_free(d_out);
     const double total_ops = ops_per_thread_iter * iters * 256.0 * blocks;
     *ops_per_sec = total_ops / (best_ms * 1e-3);
     if (seconds) *seconds = best_ms * 1e-3;
@@ -975,8 +1086,9 @@ struct DevJob {
 void release_jobs(std::vector<DevJob> &jobs, int restore_dev) {
     for (auto &j : jobs) {
         cudaSetDevice(j.dev);
+        if (j.st) cudaStreamSynchronize(j.st);
         if (j.plan) apm_plan_destroy(j.plan);
-        if (j.d_text) cudaFree(j.d_text);
+        if (j.d_text) dev_free(j.d_text);
         if (j.st) cudaStreamDestroy(j.st);
     }
     jobs.clear();
@@ -996,11 +1108,18 @@ int copy_range_to_device(const TextSource &src, long long b0, long long b1, uint
         return APM_OK;
     }
     // file: pread into two pinned staging buffers, async H2D, so disk/page-cache reads overlap the copy
-    const size_t chunk = (size_t)32 << 20;
+    const size_t chunk = kPinnedChunk;
+    static std::mutex ingest_mu;  // one ingest at a time per process: the staging buffers are shared
+    std::lock_guard<std::mutex> ingest_lk(ingest_mu);
     uint8_t *pin[2] = {nullptr, nullptr};
     cudaEvent_t done[2];
-    CUDA_TRY(cudaMallocHost((void **)&pin[0], chunk));
-    CUDA_TRY(cudaMallocHost((void **)&pin[1], chunk));
+    {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        for (int i = 0; i < 2; ++i) {
+            if (!g_pool.pinned[i]) CUDA_TRY(cudaMallocHost((void **)&g_pool.pinned[i], chunk));
+            pin[i] = g_pool.pinned[i];
+        }
+    }
     CUDA_TRY(cudaEventCreate(&done[0]));
     CUDA_TRY(cudaEventCreate(&done[1]));
     int rc = APM_OK, s = 0;
@@ -1027,8 +1146,6 @@ int copy_range_to_device(const TextSource &src, long long b0, long long b1, uint
     cudaStreamSynchronize(st);
     cudaEventDestroy(done[0]);
     cudaEventDestroy(done[1]);
-    cudaFreeHost(pin[0]);
-    cudaFreeHost(pin[1]);
     return rc;
 }
 
@@ -1053,6 +1170,17 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
     if (shard == SHARD_PATTERNS) G = std::min(G, nb_patterns);
     if (shard == SHARD_DB) G = (int)std::min<long long>(G, W);
 
+    // APM_TRACE=1: wall-clock of every phase of the one-shot call on stderr (synchronising after each phase)
+    static const bool trace = getenv("APM_TRACE") && atoi(getenv("APM_TRACE")) > 0;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what, cudaStream_t st) {
+        if (!trace) return;
+        if (st) cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[apm trace] %-22s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
+
     int restore = 0;
     cudaGetDevice(&restore);
     std::vector<DevJob> jobs(G);
@@ -1068,7 +1196,9 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
         if (cudaSetDevice(j.dev) != cudaSuccess) return bail(fail(APM_ECUDA, "cudaSetDevice(%d) failed", j.dev));
         if (cudaStreamCreateWithFlags(&j.st, cudaStreamNonBlocking) != cudaSuccess)
             return bail(fail(APM_ECUDA, "cudaStreamCreate failed on device %d", g));
+        mark("stream create", nullptr);
         if ((rc = apm_plan_create(patterns, pattern_len, nb_patterns, approx_factor, &j.plan))) return bail(rc);
+        mark("plan create", nullptr);
         if (shard == SHARD_PATTERNS) {
             if (G > 1 && (rc = apm_plan_set_pattern_shard(j.plan, g, G))) return bail(rc);
             j.j0 = 0;
@@ -1079,12 +1209,15 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
         }
         j.b0 = j.j0;
         j.b1 = std::min(N, j.j1 + mmax - 1);
-        if (cudaMalloc((void **)&j.d_text, (size_t)std::max<long long>(16, j.b1 - j.b0)) != cudaSuccess)
+        if (dev_alloc((void **)&j.d_text, (size_t)std::max<long long>(16, j.b1 - j.b0)) != cudaSuccess)
             return bail(fail(APM_ENOMEM, "cudaMalloc of %lld text bytes failed on device %d", j.b1 - j.b0, g));
+        mark("text malloc", nullptr);
         if ((rc = copy_range_to_device(src, j.b0, j.b1, j.d_text, j.st))) return bail(rc);
+        mark("text H2D", j.st);
         if ((rc = apm_plan_count_device(j.plan, j.d_text, (unsigned long long)j.b0, (unsigned long long)(j.b1 - j.b0),
                                         (unsigned long long)N, (unsigned long long)j.j0, (unsigned long long)j.j1, j.st)))
             return bail(rc);
+        mark("count kernels", j.st);
     }
     // ---- combine the per-GPU count vectors
     bool reduced_on_device = false;
@@ -1123,7 +1256,9 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
         if ((rc = apm_plan_read_counts(jobs[g].plan, part.data(), jobs[g].st))) return bail(rc);
         for (int i = 0; i < nb_patterns; ++i) n_matches[i] += part[i];
     }
+    mark("reduce + D2H", nullptr);
     release_jobs(jobs, restore);
+    mark("release", nullptr);
     return APM_OK;
 }
 

@@ -524,3 +524,21 @@ def test_one_shot_api_two_gpus_single_process():
         for shard in ("db", "patterns", "auto"):
             apm_b200.set_option("shard", shard)
             assert apm_b200.count_matches(text, pats, k) == want, (reduce, shard)
+
+
+def test_device_memory_cache_release_and_limits():
+    """The library reuses device blocks between calls; releasing the cache or disabling it changes nothing."""
+    text = oracle.synth_text(0x5EED0001, 77, 400_000).tobytes()
+    pats = [text[1000:1064], text[5000:5200], text[-20:] + b"ACGTTT"]
+    want = apm_b200.count_matches(text, pats, 3)
+    assert apm_b200.count_matches(text, pats, 3) == want
+    apm_b200.release_cache()
+    assert apm_b200.count_matches(text, pats, 3) == want
+    apm_b200.set_option("cache_mb", "0")
+    try:
+        assert apm_b200.count_matches(text, pats, 3) == want
+        assert apm_b200.count_matches(text, pats, 3) == want
+    finally:
+        apm_b200.set_option("cache_mb", "4096")
+    apm_b200.set_option("kernel", "dp")
+    assert apm_b200.count_matches(text[:50_000], pats, 3) == oracle.count_matches(text[:50_000], pats, 3)

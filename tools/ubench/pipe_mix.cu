@@ -18,7 +18,8 @@ __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
 }
 
 // MODE: 0 = LOP3 only; 1 = NL LOP3 + NI IMAD(mult uniform); 2 = same with the multiplier in a vector register
-template <int NL, int NI, int MODE>
+// SHARE: the LOP3s of a group read the same two registers in the same operand slots (operand reuse cache)
+template <int NL, int NI, int MODE, int SHARE = 0>
 __global__ void __launch_bounds__(128, 3) mix_kernel(uint32_t *out, int iters, uint32_t mul_u, uint32_t seed) {
     constexpr int NR = 48;
     uint32_t r[NR];
@@ -34,7 +35,9 @@ __global__ void __launch_bounds__(128, 3) mix_kernel(uint32_t *out, int iters, u
 #pragma unroll
             for (int l = 0; l < NL; ++l) {
                 const int d = (b + l) % NR;
-                r[d] = lop3<0xE0 + 0>(r[d], r[(d + 17) % NR], r[(d + 29) % NR]);
+                if (SHARE == 0) r[d] = lop3<0xE0 + 0>(r[d], r[(d + 17) % NR], r[(d + 29) % NR]);
+                else if (SHARE == 1) r[d] = lop3<0xE0 + 0>(r[d], r[(b + 17) % NR], r[(b + 29) % NR]);
+                else r[d] = lop3<0xE0 + 0>(r[d], r[(d + 17) % NR], r[(b + 29) % NR]);
             }
 #pragma unroll
             for (int l = 0; l < NI; ++l) {
@@ -49,12 +52,12 @@ __global__ void __launch_bounds__(128, 3) mix_kernel(uint32_t *out, int iters, u
     if (x == 0x12345678u) out[0] = x;
 }
 
-template <int NL, int NI, int MODE>
+template <int NL, int NI, int MODE, int SHARE = 0>
 void run(const char *name) {
     uint32_t *d;
     cudaMalloc(&d, 4);
     const int iters = 20000;
-    auto k = mix_kernel<NL, NI, MODE>;
+    auto k = mix_kernel<NL, NI, MODE, SHARE>;
     k<<<148 * 3, 128>>>(d, 100, 0xFFFFFFFFu, 12345u);
     cudaDeviceSynchronize();
     cudaEvent_t e0, e1;
@@ -84,6 +87,13 @@ int main() {
     run<4, 1, 1>("lop3 + imad(uniform mult)");
     run<4, 4, 1>("lop3 + imad(uniform mult)");
     run<4, 4, 2>("lop3 + imad(vector mult)");
+    run<5, 0, 0, 1>("lop3 only, 2 shared operands");
+    run<4, 3, 1, 1>("lop3(2 shared) + imad(uniform)");
+    run<4, 2, 1, 1>("lop3(2 shared) + imad(uniform)");
+    run<4, 4, 1, 1>("lop3(2 shared) + imad(uniform)");
+    run<5, 0, 0, 2>("lop3 only, 1 shared operand");
+    run<4, 3, 1, 2>("lop3(1 shared) + imad(uniform)");
+    run<4, 2, 1, 2>("lop3(1 shared) + imad(uniform)");
     run<0, 4, 1>("imad only (uniform mult)");
     run<0, 4, 2>("imad only (vector mult)");
     return 0;
