@@ -1077,7 +1077,7 @@ int nccl_comms_for(const std::vector<int> &devs) {
 
 struct DevJob {
     int dev = 0;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, copy_st = nullptr;  // count kernels / H2D copies of the file ingest
     apm_plan *plan = nullptr;
     uint8_t *d_text = nullptr;
     long long j0 = 0, j1 = 0, b0 = 0, b1 = 0;  // window-start range and byte range (global)
@@ -1090,6 +1090,7 @@ void release_jobs(std::vector<DevJob> &jobs, int restore_dev) {
         if (j.plan) apm_plan_destroy(j.plan);
         if (j.d_text) dev_free(j.d_text);
         if (j.st) cudaStreamDestroy(j.st);
+        if (j.copy_st) cudaStreamDestroy(j.copy_st);
     }
     jobs.clear();
     cudaSetDevice(restore_dev);
@@ -1101,13 +1102,19 @@ struct TextSource {
     int fd = -1;
 };
 
-int copy_range_to_device(const TextSource &src, long long b0, long long b1, uint8_t *d_dst, cudaStream_t st) {
+// Loads the global bytes [b0, b1) into d_dst.  Host buffer: one async copy on `st`.  File: pread into two pinned
+// staging buffers (cached in the pool) + async H2D on `copy_st`, so page-cache / disk reads overlap the copies;
+// after every chunk `on_chunk(bytes_end, event)` is called with the global end of the bytes enqueued so far and
+// an event recorded behind that chunk's copy -- the caller starts counting the windows that are complete while
+// the next chunk is still being read (ingest overlapped with counting).
+extern "C++" template <typename OnChunk>
+int copy_range_to_device(const TextSource &src, long long b0, long long b1, uint8_t *d_dst, cudaStream_t st,
+                         cudaStream_t copy_st, OnChunk on_chunk) {
     if (b1 <= b0) return APM_OK;
     if (src.host) {
         CUDA_TRY(cudaMemcpyAsync(d_dst, src.host + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
         return APM_OK;
     }
-    // file: pread into two pinned staging buffers, async H2D, so disk/page-cache reads overlap the copy
     const size_t chunk = kPinnedChunk;
     static std::mutex ingest_mu;  // one ingest at a time per process: the staging buffers are shared
     std::lock_guard<std::mutex> ingest_lk(ingest_mu);
@@ -1120,8 +1127,8 @@ int copy_range_to_device(const TextSource &src, long long b0, long long b1, uint
             pin[i] = g_pool.pinned[i];
         }
     }
-    CUDA_TRY(cudaEventCreate(&done[0]));
-    CUDA_TRY(cudaEventCreate(&done[1]));
+    CUDA_TRY(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
     int rc = APM_OK, s = 0;
     bool used[2] = {false, false};
     for (long long pos = b0; pos < b1 && !rc; s ^= 1) {
@@ -1137,13 +1144,14 @@ int copy_range_to_device(const TextSource &src, long long b0, long long b1, uint
             got += (size_t)r;
         }
         if (rc) break;
-        cudaError_t e = cudaMemcpyAsync(d_dst + (pos - b0), pin[s], want, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaEventRecord(done[s], st);
+        cudaError_t e = cudaMemcpyAsync(d_dst + (pos - b0), pin[s], want, cudaMemcpyHostToDevice, copy_st);
+        if (e == cudaSuccess) e = cudaEventRecord(done[s], copy_st);
         if (e != cudaSuccess) rc = fail(APM_ECUDA, "H2D copy: %s", cudaGetErrorString(e));
         used[s] = true;
         pos += (long long)want;
+        if (!rc) rc = on_chunk(pos, done[s]);
     }
-    cudaStreamSynchronize(st);
+    cudaStreamSynchronize(copy_st);
     cudaEventDestroy(done[0]);
     cudaEventDestroy(done[1]);
     return rc;
@@ -1194,7 +1202,8 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
         DevJob &j = jobs[g];
         j.dev = (restore + g) % ndev;  // the current device first
         if (cudaSetDevice(j.dev) != cudaSuccess) return bail(fail(APM_ECUDA, "cudaSetDevice(%d) failed", j.dev));
-        if (cudaStreamCreateWithFlags(&j.st, cudaStreamNonBlocking) != cudaSuccess)
+        if (cudaStreamCreateWithFlags(&j.st, cudaStreamNonBlocking) != cudaSuccess ||
+            (!src.host && cudaStreamCreateWithFlags(&j.copy_st, cudaStreamNonBlocking) != cudaSuccess))
             return bail(fail(APM_ECUDA, "cudaStreamCreate failed on device %d", g));
         mark("stream create", nullptr);
         if ((rc = apm_plan_create(patterns, pattern_len, nb_patterns, approx_factor, &j.plan))) return bail(rc);
@@ -1212,10 +1221,24 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
         if (dev_alloc((void **)&j.d_text, (size_t)std::max<long long>(16, j.b1 - j.b0)) != cudaSuccess)
             return bail(fail(APM_ENOMEM, "cudaMalloc of %lld text bytes failed on device %d", j.b1 - j.b0, g));
         mark("text malloc", nullptr);
-        if ((rc = copy_range_to_device(src, j.b0, j.b1, j.d_text, j.st))) return bail(rc);
-        mark("text H2D", j.st);
-        if ((rc = apm_plan_count_device(j.plan, j.d_text, (unsigned long long)j.b0, (unsigned long long)(j.b1 - j.b0),
-                                        (unsigned long long)N, (unsigned long long)j.j0, (unsigned long long)j.j1, j.st)))
+        // file source: the windows whose bytes (incl. the m_max - 1 halo) have arrived are counted on j.st while
+        // the host is still reading the next chunk; only the tail of the shard waits for the last chunk
+        long long counted_to = j.j0;
+        auto on_chunk = [&](long long bytes_end, cudaEvent_t ev) -> int {
+            const long long w_end = bytes_end >= j.b1 ? j.j1 : std::min(j.j1, bytes_end - (mmax - 1));
+            if (w_end - counted_to < (bytes_end >= j.b1 ? 1 : (long long)(8 << 20))) return APM_OK;  // batch small steps
+            if (cudaStreamWaitEvent(j.st, ev, 0) != cudaSuccess) return fail(APM_ECUDA, "cudaStreamWaitEvent failed");
+            const int r = apm_plan_count_device(j.plan, j.d_text, (unsigned long long)j.b0, (unsigned long long)(j.b1 - j.b0),
+                                                (unsigned long long)N, (unsigned long long)counted_to,
+                                                (unsigned long long)w_end, j.st);
+            counted_to = w_end;
+            return r;
+        };
+        if ((rc = copy_range_to_device(src, j.b0, j.b1, j.d_text, j.st, j.copy_st, on_chunk))) return bail(rc);
+        mark("text H2D", src.host ? j.st : nullptr);
+        if (counted_to < j.j1 &&
+            (rc = apm_plan_count_device(j.plan, j.d_text, (unsigned long long)j.b0, (unsigned long long)(j.b1 - j.b0),
+                                        (unsigned long long)N, (unsigned long long)counted_to, (unsigned long long)j.j1, j.st)))
             return bail(rc);
         mark("count kernels", j.st);
     }

@@ -542,3 +542,22 @@ def test_device_memory_cache_release_and_limits():
         apm_b200.set_option("cache_mb", "4096")
     apm_b200.set_option("kernel", "dp")
     assert apm_b200.count_matches(text[:50_000], pats, 3) == oracle.count_matches(text[:50_000], pats, 3)
+
+
+@pytest.mark.parametrize("mode", ["direct", "band"])
+def test_file_ingest_pipeline_multi_chunk(tmp_path, mode):
+    """apm_count_matches_file streams the file through 32 MiB pinned chunks and counts the windows that are
+    complete while the next chunk is read: same counts as the host-buffer call, with patterns planted ACROSS the
+    chunk seams (32 MiB, 64 MiB) and at the very end of the file (truncated tail windows)."""
+    n = (72 << 20) + 12345
+    text = oracle.synth_text(0x5EED0001, 4242, n).tobytes()
+    chunk = 32 << 20
+    pats = [text[chunk - 30:chunk + 34], text[2 * chunk - 1:2 * chunk + 63], text[chunk - 199:chunk + 1],
+            text[5_000_000:5_000_050], text[-40:] + b"ACGTACGTACGT", text[chunk + 7:chunk + 39]]
+    f = tmp_path / "big.fa"
+    f.write_bytes(text)
+    apm_b200.set_option("mode", mode)
+    k = 3
+    want = apm_b200.count_matches(text, pats, k)
+    assert all(w >= 1 for w in want)
+    assert apm_b200.count_matches_file(str(f), pats, k) == want
