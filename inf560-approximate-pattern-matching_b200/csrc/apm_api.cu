@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 #include <chrono>
+#include <climits>
 #include <map>
 #include <dlfcn.h>
 #include <fcntl.h>
@@ -27,6 +28,7 @@
 #include "apm_myers.cuh"
 #include "apm_sliced.cuh"
 #include "apm_band.cuh"
+#include "apm_filter.cuh"
 #include "apm_util_kernels.cuh"
 
 using namespace apm;
@@ -55,7 +57,7 @@ int fail(int code, const char *fmt, ...) {
 
 enum { SHARD_AUTO = 0, SHARD_DB = 1, SHARD_PATTERNS = 2 };
 enum { KERNEL_AUTO = 0, KERNEL_MYERS = 1, KERNEL_DP = 2, KERNEL_SLICED = 3 };
-enum { MODE_DIRECT = 0, MODE_BAND = 1 };
+enum { MODE_DIRECT = 0, MODE_BAND = 1, MODE_FILTER = 2 };
 
 struct Options {
     int gpus = 1;  // 0 = all
@@ -68,6 +70,7 @@ struct Options {
     int cell = -1;   // DP-cell code of the sliced/band kernels: -1 auto, 0 = 5 LOP3, 1 = 4 LOP3 + 3 IMAD, 2 = 4 LOP3 + 2 IMAD
     int reduce = 0;  // multi-GPU count reduction: 0 auto (NCCL when loadable), 1 nccl, 2 host sum
     long long dp_scratch_mb = 256;
+    long long filter_cand_mb = 128;  // candidate buffer of the seed filter (mode=filter), MiB
     long long cache_mb = 4096;  // device memory kept for reuse between calls (dev_alloc / dev_free)
 };
 std::mutex g_opt_mu;
@@ -228,6 +231,21 @@ struct SlicedList {
     size_t smem_set[3] = {0, 0, 0};
 };
 
+
+// patterns handled by the exact seed filter (apm_filter.cuh) and its device tables
+struct FilterSet {
+    std::vector<int> ids;  // pattern indices, slot order
+    int s = 0, hb = 0, nent = 0, mmax = 0, mmin = 0;
+    uint32_t bs = 0;
+    uint32_t *d_bitmap = nullptr, *d_ent_idx = nullptr, *d_ent_slot = nullptr;
+    uint8_t *d_ent_piece = nullptr;
+    int *d_fp_id = nullptr, *d_fp_m = nullptr;
+    long long *d_fp_off = nullptr;
+    uint64_t *d_cand = nullptr;
+    unsigned long long cap = 0;
+    unsigned long long *d_ctr = nullptr;  // [0] candidates, [1] (low word) overflow flag
+};
+
 template <typename T>
 int upload(T **dptr, const std::vector<T> &h) {
     *dptr = nullptr;
@@ -247,6 +265,11 @@ struct apm_plan {
     int shard_rank = 0, shard_world = 1;
     std::vector<Bucket> buckets;
     std::vector<SlicedList> sliced;
+    // mode=filter: patterns handled by the seed filter; fb_* = the same patterns as ordinary kernel lists, launched
+    // behind the filter and gated on its overflow flag
+    FilterSet filter;
+    std::vector<Bucket> fb_buckets;
+    std::vector<SlicedList> fb_sliced;
     int nplanes = 0;
     uint8_t *d_plane_of = nullptr;
     std::vector<int> tail_list, all_list;
@@ -261,21 +284,37 @@ struct apm_plan {
 
 namespace {
 
-void free_work(apm_plan *pl) {
-    for (auto &b : pl->buckets) {
+void free_lists(std::vector<Bucket> &buckets, std::vector<SlicedList> &sliced) {
+    for (auto &b : buckets) {
         dev_free(b.d_peq);
         dev_free(b.d_group_m);
         dev_free(b.d_group_pat);
     }
-    pl->buckets.clear();
-    for (auto &l : pl->sliced) {
+    buckets.clear();
+    for (auto &l : sliced) {
         dev_free(l.d_codes);
         dev_free(l.d_m);
         dev_free(l.d_id);
         dev_free(l.d_vscratch);
         dev_free(l.d_work);
     }
-    pl->sliced.clear();
+    sliced.clear();
+}
+
+void free_work(apm_plan *pl) {
+    free_lists(pl->buckets, pl->sliced);
+    free_lists(pl->fb_buckets, pl->fb_sliced);
+    FilterSet &f = pl->filter;
+    dev_free(f.d_bitmap);
+    dev_free(f.d_ent_idx);
+    dev_free(f.d_ent_slot);
+    dev_free(f.d_ent_piece);
+    dev_free(f.d_fp_id);
+    dev_free(f.d_fp_m);
+    dev_free(f.d_fp_off);
+    dev_free(f.d_cand);
+    dev_free(f.d_ctr);
+    f = FilterSet();
     dev_free(pl->d_tail_list);
     dev_free(pl->d_all_list);
     pl->d_tail_list = pl->d_all_list = nullptr;
@@ -285,30 +324,17 @@ void free_work(apm_plan *pl) {
 
 int auto_rblock(int NW) { return NW <= 2 ? 4 : (NW <= 4 ? 2 : 1); }
 
-// (Re)build buckets / DP lists for the active patterns (pattern shard) and upload them.
-int build_work(apm_plan *pl) {
-    free_work(pl);
+// Kernel lists (row-parallel buckets by word count, window-sliced lists by register-block width) for the
+// bit-parallel patterns `ids`, uploaded to the device.
+int build_lists(apm_plan *pl, const std::vector<int> &ids_in, std::vector<Bucket> &buckets, std::vector<SlicedList> &sliced) {
     std::vector<std::vector<int>> by_nw(kMaxWords + 1);
     std::vector<int> sliced_ids[2];
-    pl->tail_width = pl->tail_mmax = pl->all_mmax = 0;
-    for (int p = 0; p < pl->P; ++p) {
-        if (p % pl->shard_world != pl->shard_rank) continue;
+    for (int p : ids_in) {
         const int m = (int)pl->pats[p].size();
         const bool sliced_ok = m <= kSlicedMaxLen && pl->nplanes <= kSlicedMaxPlanes &&
                                (pl->opt.kernel == KERNEL_SLICED || pl->opt.kernel == KERNEL_AUTO);
-        if (pl->opt.kernel == KERNEL_DP || (m > kMaxMyersLen && !sliced_ok)) {
-            pl->all_list.push_back(p);
-            pl->all_mmax = std::max(pl->all_mmax, m);
-            continue;
-        }
         if (sliced_ok) sliced_ids[m <= 32 ? 0 : 1].push_back(p);
         else by_nw[(m + 31) / 32].push_back(p);
-        const int tw = m - 1 - pl->k;  // number of truncated tail windows (sequential.c:121,131-134)
-        if (tw > 0) {
-            pl->tail_list.push_back(p);
-            pl->tail_width = std::max(pl->tail_width, tw);
-            pl->tail_mmax = std::max(pl->tail_mmax, m);
-        }
     }
     for (int NW = 1; NW <= kMaxWords; ++NW) {
         auto &ids = by_nw[NW];
@@ -347,7 +373,7 @@ int build_work(apm_plan *pl) {
         if ((rc = upload(&b.d_peq, b.peq))) return rc;
         if ((rc = upload(&b.d_group_m, b.group_m))) return rc;
         if ((rc = upload(&b.d_group_pat, b.group_pat))) return rc;
-        pl->buckets.push_back(std::move(b));
+        buckets.push_back(std::move(b));
     }
     for (int which = 0; which < 2; ++which) {
         auto &ids = sliced_ids[which];
@@ -371,9 +397,111 @@ int build_work(apm_plan *pl) {
         if ((rc2 = upload(&l.d_codes, l.codes))) return rc2;
         if ((rc2 = upload(&l.d_m, l.m))) return rc2;
         if ((rc2 = upload(&l.d_id, l.id))) return rc2;
-        pl->sliced.push_back(std::move(l));
+        sliced.push_back(std::move(l));
+    }
+    return APM_OK;
+}
+
+// Seed tables of the exact filter (apm_filter.cuh) for the patterns f.ids.
+int build_filter(apm_plan *pl) {
+    FilterSet &f = pl->filter;
+    const int k = pl->k;
+    f.s = kFilterMaxSeed;
+    f.mmax = 0;
+    f.mmin = INT_MAX;
+    for (int p : f.ids) {
+        const int m = (int)pl->pats[p].size();
+        f.s = std::min(f.s, m / (k + 1));
+        f.mmax = std::max(f.mmax, m);
+        f.mmin = std::min(f.mmin, m);
+    }
+    f.nent = (int)f.ids.size() * (k + 1);
+    int lg = 0;
+    while ((1ll << lg) < f.nent) ++lg;
+    f.hb = std::max(20, std::min(27, lg + 9));  // <= 1/512 of the bitmap set: the scan rarely leaves its fast path
+    f.bs = 1u;
+    for (int i = 0; i < f.s; ++i) f.bs *= kFilterHashB;
+    std::vector<uint32_t> bitmap((size_t)1 << (f.hb - 5), 0u);
+    struct Ent { uint32_t idx, slot; uint8_t piece; };
+    std::vector<Ent> ents;
+    ents.reserve((size_t)f.nent);
+    std::vector<int> fp_id, fp_m;
+    std::vector<long long> fp_off;
+    long long off = 0;
+    std::vector<long long> all_off(pl->P);
+    for (int p = 0; p < pl->P; ++p) {
+        all_off[p] = off;
+        off += (long long)pl->pats[p].size();
+    }
+    for (size_t slot = 0; slot < f.ids.size(); ++slot) {
+        const int p = f.ids[slot];
+        const std::string &pat = pl->pats[p];
+        const int m = (int)pat.size();
+        fp_id.push_back(p);
+        fp_m.push_back(m);
+        fp_off.push_back(all_off[p]);
+        for (int i = 0; i <= k; ++i) {
+            const int o = filter_piece_offset(i, m, k);
+            const uint32_t idx = filter_index(filter_hash((const uint8_t *)pat.data() + o, f.s), f.hb);
+            bitmap[idx >> 5] |= 1u << (idx & 31);
+            ents.push_back({idx, (uint32_t)slot, (uint8_t)i});
+        }
+    }
+    std::stable_sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) { return a.idx < b.idx; });
+    std::vector<uint32_t> e_idx, e_slot;
+    std::vector<uint8_t> e_piece;
+    for (auto &e : ents) {
+        e_idx.push_back(e.idx);
+        e_slot.push_back(e.slot);
+        e_piece.push_back(e.piece);
     }
     int rc;
+    if ((rc = upload(&f.d_bitmap, bitmap))) return rc;
+    if ((rc = upload(&f.d_ent_idx, e_idx))) return rc;
+    if ((rc = upload(&f.d_ent_slot, e_slot))) return rc;
+    if ((rc = upload(&f.d_ent_piece, e_piece))) return rc;
+    if ((rc = upload(&f.d_fp_id, fp_id))) return rc;
+    if ((rc = upload(&f.d_fp_m, fp_m))) return rc;
+    if ((rc = upload(&f.d_fp_off, fp_off))) return rc;
+    f.cap = (unsigned long long)std::max<long long>(1, pl->opt.filter_cand_mb) * ((1ull << 20) / sizeof(uint64_t));
+    CUDA_TRY(dev_alloc((void **)&f.d_cand, f.cap * sizeof(uint64_t)));
+    CUDA_TRY(dev_alloc((void **)&f.d_ctr, 2 * sizeof(unsigned long long)));
+    return APM_OK;
+}
+
+// (Re)build buckets / DP lists for the active patterns (pattern shard) and upload them.
+int build_work(apm_plan *pl) {
+    free_work(pl);
+    std::vector<int> main_ids, filter_ids;
+    pl->tail_width = pl->tail_mmax = pl->all_mmax = 0;
+    for (int p = 0; p < pl->P; ++p) {
+        if (p % pl->shard_world != pl->shard_rank) continue;
+        const int m = (int)pl->pats[p].size();
+        const bool sliced_ok = m <= kSlicedMaxLen && pl->nplanes <= kSlicedMaxPlanes &&
+                               (pl->opt.kernel == KERNEL_SLICED || pl->opt.kernel == KERNEL_AUTO);
+        if (pl->opt.kernel == KERNEL_DP || (m > kMaxMyersLen && !sliced_ok)) {
+            pl->all_list.push_back(p);
+            pl->all_mmax = std::max(pl->all_mmax, m);
+            continue;
+        }
+        // exact seed filter: worth it when every piece of the pattern still holds a selective seed
+        const bool filtered = pl->opt.mode == MODE_FILTER && pl->k <= kFilterMaxK && m / (pl->k + 1) >= kFilterMinSeed &&
+                              filter_ids.size() < ((size_t)1 << 24);
+        (filtered ? filter_ids : main_ids).push_back(p);
+        const int tw = m - 1 - pl->k;  // number of truncated tail windows (sequential.c:121,131-134)
+        if (tw > 0) {
+            pl->tail_list.push_back(p);
+            pl->tail_width = std::max(pl->tail_width, tw);
+            pl->tail_mmax = std::max(pl->tail_mmax, m);
+        }
+    }
+    int rc;
+    if ((rc = build_lists(pl, main_ids, pl->buckets, pl->sliced))) return rc;
+    if (!filter_ids.empty()) {
+        if ((rc = build_lists(pl, filter_ids, pl->fb_buckets, pl->fb_sliced))) return rc;
+        pl->filter.ids = filter_ids;
+        if ((rc = build_filter(pl))) return rc;
+    }
     if ((rc = upload(&pl->d_tail_list, pl->tail_list))) return rc;
     if ((rc = upload(&pl->d_all_list, pl->all_list))) return rc;
     return APM_OK;
@@ -393,7 +521,7 @@ int ensure_scratch(apm_plan *pl, size_t bytes) {
 }
 
 int launch_myers(apm_plan *pl, Bucket &b, const uint8_t *d_buf, long long buf_len, long long n_end,
-                 long long w0, long long w1, cudaStream_t st) {
+                 long long w0, long long w1, cudaStream_t st, const unsigned int *run_if = nullptr) {
     // windows of the shortest pattern of the bucket that are full-length
     const long long lim = std::min(w1, n_end - b.mmin + 1);
     if (lim <= w0) return APM_OK;
@@ -442,6 +570,7 @@ int launch_myers(apm_plan *pl, Bucket &b, const uint8_t *d_buf, long long buf_le
     a.tile = tile;
     a.c_one = 1u;
     a.c_two = 2u;
+    a.run_if = run_if;
     b.fn<<<dim3(gx, gy), kThreads, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     g_launches++;
@@ -541,7 +670,7 @@ int launch_band(apm_plan *pl, SlicedList &l, SlicedArgs a, long long nwin, cudaS
 }
 
 int launch_sliced(apm_plan *pl, SlicedList &l, const uint8_t *d_buf, long long buf_len, long long n_end, long long w0,
-                  long long w1, cudaStream_t st) {
+                  long long w1, cudaStream_t st, const unsigned int *run_if = nullptr) {
     const long long lim = std::min(w1, n_end - l.mmin + 1);
     if (lim <= w0) return APM_OK;
     SlicedArgs a;
@@ -566,10 +695,11 @@ int launch_sliced(apm_plan *pl, SlicedList &l, const uint8_t *d_buf, long long b
     a.row_cols = 32;
     a.lead = 0;
     a.work_counter = nullptr;
+    a.run_if = run_if;
     a.c_neg1 = 0xFFFFFFFFu;
     // exact band mode: only the 2K+1 diagonals that can matter for D <= k (worth it when the band is
     // narrower than the matrix)
-    if (pl->opt.mode == MODE_BAND && pl->k <= kBandMaxK && 2 * pl->k + 1 < l.mmin)
+    if (pl->opt.mode != MODE_DIRECT && pl->k <= kBandMaxK && 2 * pl->k + 1 < l.mmin)
         return launch_band(pl, l, a, lim - w0, st);
     // auto: measured on B200 (profiles/r01_quick_cell_variants.jsonl) -- the FMA-pipe variants win where the whole
     // pattern is one register block (m <= 32: 4 LOP3 + 2 IMAD, m <= 64: 4 LOP3 + 3 IMAD); register-file operand
@@ -580,6 +710,74 @@ int launch_sliced(apm_plan *pl, SlicedList &l, const uint8_t *d_buf, long long b
     if (cell == 1)
         return l.MC == 32 ? launch_sliced_mc<32, 1>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 1>(pl, l, a, lim - w0, st);
     return l.MC == 32 ? launch_sliced_mc<32, 0>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 0>(pl, l, a, lim - w0, st);
+}
+
+// mode=filter: seed scan + verification of the filtered patterns over window starts [w0, w1) (local
+// coordinates), in rounds of 2^27 windows; behind every round the same patterns' ordinary kernels are launched
+// gated on the round's overflow flag (they run only when the candidate buffer was too small).  Stream ordered.
+template <int S>
+void launch_filter_scan(const FilterArgs &a, unsigned blocks, cudaStream_t st) {
+    filter_scan_kernel<S><<<blocks, kFilterThreads, 0, st>>>(a);
+}
+
+int launch_filter(apm_plan *pl, const uint8_t *d_buf, long long buf_len, long long n_end, long long w0, long long w1,
+                  cudaStream_t st) {
+    FilterSet &f = pl->filter;
+    const long long lim = std::min(w1, n_end - f.mmin + 1);  // full windows only
+    if (f.ids.empty() || lim <= w0) return APM_OK;
+    FilterArgs a;
+    a.buf = d_buf;
+    a.buf_len = buf_len;
+    a.n_end = n_end;
+    a.s = f.s;
+    a.k = pl->k;
+    a.hb = f.hb;
+    a.mmax = f.mmax;
+    a.bs = f.bs;
+    a.bitmap = f.d_bitmap;
+    a.ent_idx = f.d_ent_idx;
+    a.ent_slot = f.d_ent_slot;
+    a.ent_piece = f.d_ent_piece;
+    a.nent = f.nent;
+    a.fp_id = f.d_fp_id;
+    a.fp_m = f.d_fp_m;
+    a.fp_off = f.d_fp_off;
+    a.pat_bytes = pl->d_pat_bytes;
+    a.cand = f.d_cand;
+    a.cap = f.cap;
+    a.ncand = f.d_ctr;
+    a.overflow = reinterpret_cast<unsigned int *>(f.d_ctr + 1);
+    a.counts = pl->d_counts;
+    const long long round = 1ll << kFilterSlabLog;
+    for (long long r0 = w0; r0 < lim; r0 += round) {
+        a.w0 = r0;
+        a.w1 = std::min(lim, r0 + round);
+        CUDA_TRY(cudaMemsetAsync(f.d_ctr, 0, 2 * sizeof(unsigned long long), st));
+        const long long positions = a.w1 - a.w0 + f.mmax;
+        const long long tiles = (positions + kFilterThreads * kFilterPosPerThread - 1) / (kFilterThreads * kFilterPosPerThread);
+        const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(tiles, (long long)pl->num_sms * 16));
+        switch (f.s) {
+            case 8: launch_filter_scan<8>(a, blocks, st); break;
+            case 9: launch_filter_scan<9>(a, blocks, st); break;
+            case 10: launch_filter_scan<10>(a, blocks, st); break;
+            case 11: launch_filter_scan<11>(a, blocks, st); break;
+            case 12: launch_filter_scan<12>(a, blocks, st); break;
+            case 13: launch_filter_scan<13>(a, blocks, st); break;
+            case 14: launch_filter_scan<14>(a, blocks, st); break;
+            case 15: launch_filter_scan<15>(a, blocks, st); break;
+            default: launch_filter_scan<16>(a, blocks, st); break;
+        }
+        CUDA_TRY(cudaGetLastError());
+        filter_verify_kernel<<<pl->num_sms * 8, 128, 0, st>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 2;
+        int rc;
+        for (auto &b : pl->fb_buckets)
+            if ((rc = launch_myers(pl, b, d_buf, buf_len, n_end, a.w0, a.w1, st, a.overflow))) return rc;
+        for (auto &l : pl->fb_sliced)
+            if ((rc = launch_sliced(pl, l, d_buf, buf_len, n_end, a.w0, a.w1, st, a.overflow))) return rc;
+    }
+    return APM_OK;
 }
 
 int launch_dp(apm_plan *pl, const uint8_t *d_buf, long long buf_offset, long long n_total, long long j_begin,
@@ -735,6 +933,7 @@ int apm_set_option(const char *key, const char *value) {
     } else if (k == "mode") {
         if (v == "direct") g_opt.mode = MODE_DIRECT;
         else if (v == "band") g_opt.mode = MODE_BAND;
+        else if (v == "filter") g_opt.mode = MODE_FILTER;
         else return bad();
     } else if (k == "rblock") {
         if (v == "auto") g_opt.rblock = 0;
@@ -761,6 +960,10 @@ int apm_set_option(const char *key, const char *value) {
         else if (v == "nccl") g_opt.reduce = 1;
         else if (v == "host") g_opt.reduce = 2;
         else return bad();
+    } else if (k == "filter_cand_mb") {
+        long long mb = atoll(value);
+        if (mb < 1 || mb > 16384) return bad();
+        g_opt.filter_cand_mb = mb;
     } else if (k == "cache_mb") {
         long long mb = atoll(value);
         if (v.empty() || v.find_first_not_of("0123456789") != std::string::npos || mb > (1ll << 20)) return bad();
@@ -783,12 +986,13 @@ const char *apm_get_option(const char *key) {
     else if (k == "shard") tl_optbuf = o.shard == SHARD_DB ? "db" : (o.shard == SHARD_PATTERNS ? "patterns" : "auto");
     else if (k == "kernel")
         tl_optbuf = o.kernel == KERNEL_DP ? "dp" : (o.kernel == KERNEL_MYERS ? "myers" : (o.kernel == KERNEL_SLICED ? "sliced" : "auto"));
-    else if (k == "mode") tl_optbuf = o.mode == MODE_BAND ? "band" : "direct";
+    else if (k == "mode") tl_optbuf = o.mode == MODE_FILTER ? "filter" : (o.mode == MODE_BAND ? "band" : "direct");
     else if (k == "rblock") tl_optbuf = o.rblock ? std::to_string(o.rblock) : "auto";
     else if (k == "tile") tl_optbuf = o.tile ? std::to_string(o.tile) : "auto";
     else if (k == "variant") tl_optbuf = std::to_string(o.variant);
     else if (k == "cell") tl_optbuf = o.cell == 2 ? "fma" : (o.cell == 1 ? "fma3" : (o.cell == 0 ? "lop3" : "auto"));
     else if (k == "reduce") tl_optbuf = o.reduce == 1 ? "nccl" : (o.reduce == 2 ? "host" : "auto");
+    else if (k == "filter_cand_mb") tl_optbuf = std::to_string(o.filter_cand_mb);
     else if (k == "cache_mb") tl_optbuf = std::to_string(o.cache_mb);
     else if (k == "dp_scratch_mb") tl_optbuf = std::to_string(o.dp_scratch_mb);
     else return nullptr;
@@ -952,6 +1156,9 @@ int apm_plan_count_device(apm_plan *pl, const unsigned char *d_buf, unsigned lon
         rc = launch_sliced(pl, l, d_buf, (long long)buf_len, N - (long long)buf_offset, jb - (long long)buf_offset,
                            je - (long long)buf_offset, st);
     }
+    if (!rc)
+        rc = launch_filter(pl, d_buf, (long long)buf_len, N - (long long)buf_offset, jb - (long long)buf_offset,
+                           je - (long long)buf_offset, st);
     if (!rc) rc = launch_dp(pl, d_buf, (long long)buf_offset, N, jb, je, st);
     if (cur != pl->device) cudaSetDevice(cur);
     return rc;

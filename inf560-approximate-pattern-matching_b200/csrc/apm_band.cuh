@@ -39,6 +39,7 @@ __device__ __forceinline__ const unsigned char *band_row_ptr(const unsigned char
 template <int K, int CELL>
 __global__ void __launch_bounds__(kSlicedThreads, 3) band_count_kernel(const SlicedArgs a) {
     constexpr int BW = 2 * K + 1;
+    if (a.run_if && *a.run_if == 0u) return;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const size_t off_U = sliced_smem_fixed(a.nplanes, a.rowsU);

@@ -240,6 +240,7 @@ struct MyersArgs {
     int k;                       // approx_factor
     int tile;                    // window starts per tile (multiple of kThreads)
     uint32_t c_one, c_two;       // the constants 1 and 2, opaque to ptxas (see myers_step_fma)
+    const unsigned int *run_if;  // optional gate: the whole launch is a no-op when *run_if == 0 (filter fallback)
 };
 
 // Shared-memory layout (dynamic): see myers_smem_bytes() -- the host uses the same formula.
@@ -301,6 +302,7 @@ template <int NW, int R, int V>
 __global__ void __launch_bounds__(kThreads) myers_count_kernel(const MyersArgs a) {
     constexpr int EW = entry_words(R * NW);
     constexpr int U = 8;  // text symbols per unrolled inner-loop body
+    if (a.run_if && *a.run_if == 0u) return;
     extern __shared__ __align__(128) unsigned char smem[];
 
     const int tid = threadIdx.x;

@@ -74,6 +74,7 @@ struct SlicedArgs {
     int row_cols;                // 32-bit windows stored per U row (32; 32 + 2K for the band kernel)
     int lead;                    // text positions staged BEFORE the tile start (0; 32 for the band kernel)
     unsigned long long *work_counter;  // zeroed before the launch: dynamic (tile, range) item dispenser
+    const unsigned int *run_if;  // optional gate: the whole launch is a no-op when *run_if == 0 (filter fallback)
     uint32_t c_neg1;             // the constant 0xFFFFFFFF, opaque to ptxas (multiplier of the FMA-pipe subtractions)
 };
 
@@ -350,6 +351,7 @@ __device__ __forceinline__ TileGeom sliced_stage_tile(const SlicedArgs &a, long 
 template <int MC, int CELL>
 __global__ void __launch_bounds__(kSlicedThreads, MC == 64 ? 3 : 4) sliced_count_kernel(const SlicedArgs a) {
     static_assert(MC == 32 || MC == 64, "MC must be 32 or 64");
+    if (a.run_if && *a.run_if == 0u) return;
     constexpr int LOG = MC == 32 ? 6 : 7;  // 2*MC planes are summed per block: value range [0, 2*MC]
     constexpr int NL = LOG + 1;
     extern __shared__ __align__(128) unsigned char smem[];

@@ -167,7 +167,110 @@ def test_band_mode_every_band_width(k):
     assert apm_b200.count_matches(text, pats, k) == want
     apm_b200.set_option("mode", "band")
     assert apm_b200.count_matches(text, pats, k) == want
+    apm_b200.set_option("mode", "filter")
+    assert apm_b200.count_matches(text, pats, k) == want
     assert sum(want) > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# exact filter mode (pigeonhole seeds + banded verification): bit-identical counts
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c["name"])
+def test_golden_filter_mode(case):
+    apm_b200.set_option("mode", "filter")
+    assert apm_b200.get_option("mode") == "filter"
+    before = apm_b200.launch_count()
+    assert apm_b200.count_matches(FX[case["text"]], case["patterns"], case["k"]) == case["expected"]
+    assert apm_b200.launch_count() > before
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_vs_oracle_filter_mode(seed):
+    rng = np.random.default_rng(5000 + seed)
+    text, pats, k = _random_case(rng)
+    apm_b200.set_option("mode", "filter")
+    assert apm_b200.count_matches(text, pats, k) == oracle.count_matches(text, pats, k)
+
+
+def _edited_copies_case(rng, n, lengths, k):
+    """text with copies of every pattern carrying 0..k+2 random edits (substitutions, insertions, deletions)."""
+    base = bytearray(oracle.synth_text(0x5EED0001, int(rng.integers(0, 1 << 30)), n).tobytes())
+    pats = []
+    pos = 1000
+    for m in lengths:
+        off = int(rng.integers(0, n - m))
+        p = bytes(base[off:off + m])
+        pats.append(p)
+        for e in range(0, k + 3):
+            q = bytearray(p)
+            for _ in range(e):
+                op = int(rng.integers(0, 3))
+                x = int(rng.integers(0, len(q)))
+                if op == 0:
+                    q[x] = int(rng.choice(list(b"ACGT")))
+                elif op == 1:
+                    q.insert(x, int(rng.choice(list(b"ACGT"))))
+                elif len(q) > 1:
+                    del q[x]
+            if pos + len(q) + 50 < n:
+                base[pos:pos + len(q)] = q
+                pos += len(q) + int(rng.integers(1, 40))
+    return bytes(base), pats
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_filter_mode_indels_and_shifts(seed):
+    """Copies with insertions / deletions make the verbatim piece sit at a SHIFTED offset inside the window (|shift|
+    <= k); windows near a planted copy are witnessed by several (piece, shift) pairs and must be counted once."""
+    rng = np.random.default_rng(9100 + seed)
+    k = int(rng.integers(0, 7))
+    lengths = [int(x) for x in rng.integers(8 * (k + 1), 140, size=5)] + [12, 30]
+    text, pats = _edited_copies_case(rng, 120_000, lengths, k)
+    want = oracle.count_matches(text, pats, k)
+    assert sum(want) >= len(lengths)
+    for mode in ("filter", "band", "direct"):
+        apm_b200.set_option("mode", mode)
+        assert apm_b200.count_matches(text, pats, k) == want, mode
+
+
+@pytest.mark.parametrize("cand_mb", ["1", "128"])
+def test_filter_mode_low_complexity_text_overflows_to_the_band_kernel(cand_mb):
+    """Poly-A / short-period text: every position is a seed hit of every repeat pattern.  With a 1 MiB candidate
+    buffer the scan overflows and the band kernel takes the round; the counts stay exact either way."""
+    n = 300_000
+    text = (b"A" * 100_000) + (b"ACAC" * 25_000) + oracle.synth_text(0x5EED0001, 3, 100_000).tobytes()
+    pats = [b"A" * 64, b"ACAC" * 16, b"A" * 31 + b"C" + b"A" * 32, text[250_000:250_064], b"CACA" * 10]
+    k = 3
+    apm_b200.set_option("mode", "band")
+    want = apm_b200.count_matches(text, pats, k)
+    assert want[0] > 90_000 and want[1] > 40_000
+    apm_b200.set_option("mode", "filter")
+    apm_b200.set_option("filter_cand_mb", cand_mb)
+    try:
+        assert apm_b200.count_matches(text, pats, k) == want
+    finally:
+        apm_b200.set_option("filter_cand_mb", "128")
+    assert want[:2] == oracle.count_matches(text[:n], pats[:2], k)
+
+
+def test_filter_mode_shards_and_binary_alphabet():
+    """Window-range calls (database shards) add up in filter mode; byte patterns outside ACGT use the same path."""
+    rng = np.random.default_rng(77)
+    n = 400_000
+    text = bytes(rng.integers(0, 256, size=n, dtype=np.uint8))
+    pats = [text[1000:1064], text[200_000:200_100], text[399_900:399_990], bytes(rng.integers(0, 256, size=80, dtype=np.uint8))]
+    k = 4
+    apm_b200.set_option("mode", "filter")
+    whole = apm_b200.count_matches(text, pats, k)
+    assert whole == oracle.count_matches(text, pats, k)
+    assert whole[:3] == [5, 5, 5]  # a shift by 1 or 2 positions costs 2 or 4 edits: 5 windows per planted copy at k = 4
+    torch = _torch()
+    dev = torch.tensor(np.frombuffer(text, dtype=np.uint8), device="cuda")
+    with apm_b200.Plan(pats, k) as plan:
+        cuts = [0, 1001, 1064, 200_050, 399_950, n]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            plan.count_device(dev.data_ptr(), 0, n, n, a, b)
+        assert plan.read_counts() == whole
 
 
 def test_cli_drop_in(tmp_path):
