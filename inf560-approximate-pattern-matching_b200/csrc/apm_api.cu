@@ -237,7 +237,8 @@ struct FilterSet {
     std::vector<int> ids;  // pattern indices, slot order
     int s = 0, hb = 0, nent = 0, mmax = 0, mmin = 0;
     uint32_t bs = 0;
-    uint32_t *d_bitmap = nullptr, *d_ent_idx = nullptr, *d_ent_slot = nullptr;
+    uint32_t *d_bitmap = nullptr, *d_digest = nullptr, *d_ent_idx = nullptr, *d_ent_slot = nullptr;
+    uint32_t *d_coarse = nullptr, *d_ent_hash = nullptr;
     uint8_t *d_ent_piece = nullptr;
     int *d_fp_id = nullptr, *d_fp_m = nullptr;
     long long *d_fp_off = nullptr;
@@ -306,6 +307,9 @@ void free_work(apm_plan *pl) {
     free_lists(pl->fb_buckets, pl->fb_sliced);
     FilterSet &f = pl->filter;
     dev_free(f.d_bitmap);
+    dev_free(f.d_digest);
+    dev_free(f.d_coarse);
+    dev_free(f.d_ent_hash);
     dev_free(f.d_ent_idx);
     dev_free(f.d_ent_slot);
     dev_free(f.d_ent_piece);
@@ -418,11 +422,11 @@ int build_filter(apm_plan *pl) {
     f.nent = (int)f.ids.size() * (k + 1);
     int lg = 0;
     while ((1ll << lg) < f.nent) ++lg;
-    f.hb = std::max(20, std::min(27, lg + 9));  // <= 1/512 of the bitmap set: the scan rarely leaves its fast path
+    f.hb = std::max(kFilterSmemLog + 1, std::min(27, lg + 12));  // <= 1/4096 of the bitmap set  // <= 1/512 of the bitmap set: the scan rarely leaves its fast path
     f.bs = 1u;
     for (int i = 0; i < f.s; ++i) f.bs *= kFilterHashB;
-    std::vector<uint32_t> bitmap((size_t)1 << (f.hb - 5), 0u);
-    struct Ent { uint32_t idx, slot; uint8_t piece; };
+    std::vector<uint32_t> bitmap((size_t)1 << (f.hb - 5), 0u), digest((size_t)1 << (kFilterSmemLog - 5), 0u);
+    struct Ent { uint32_t idx, hash, slot; uint8_t piece; };
     std::vector<Ent> ents;
     ents.reserve((size_t)f.nent);
     std::vector<int> fp_id, fp_m;
@@ -442,22 +446,30 @@ int build_filter(apm_plan *pl) {
         fp_off.push_back(all_off[p]);
         for (int i = 0; i <= k; ++i) {
             const int o = filter_piece_offset(i, m, k);
-            const uint32_t idx = filter_index(filter_hash((const uint8_t *)pat.data() + o, f.s), f.hb);
+            const uint32_t hash = filter_hash((const uint8_t *)pat.data() + o, f.s);
+            const uint32_t idx = filter_index(hash, f.hb);
             bitmap[idx >> 5] |= 1u << (idx & 31);
-            ents.push_back({idx, (uint32_t)slot, (uint8_t)i});
+            digest[filter_digest_word(hash)] |= filter_digest_mask(hash);
+            ents.push_back({idx, hash, (uint32_t)slot, (uint8_t)i});
         }
     }
     std::stable_sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) { return a.idx < b.idx; });
-    std::vector<uint32_t> e_idx, e_slot;
+    std::vector<uint32_t> e_idx, e_slot, e_hash, coarse(((size_t)1 << 16) + 1, 0u);
     std::vector<uint8_t> e_piece;
+    for (auto &e : ents) coarse[(e.idx >> (f.hb - 16)) + 1]++;
+    for (size_t c = 1; c < coarse.size(); ++c) coarse[c] += coarse[c - 1];
     for (auto &e : ents) {
         e_idx.push_back(e.idx);
+        e_hash.push_back(e.hash);
         e_slot.push_back(e.slot);
         e_piece.push_back(e.piece);
     }
     int rc;
     if ((rc = upload(&f.d_bitmap, bitmap))) return rc;
+    if ((rc = upload(&f.d_digest, digest))) return rc;
     if ((rc = upload(&f.d_ent_idx, e_idx))) return rc;
+    if ((rc = upload(&f.d_ent_hash, e_hash))) return rc;
+    if ((rc = upload(&f.d_coarse, coarse))) return rc;
     if ((rc = upload(&f.d_ent_slot, e_slot))) return rc;
     if ((rc = upload(&f.d_ent_piece, e_piece))) return rc;
     if ((rc = upload(&f.d_fp_id, fp_id))) return rc;
@@ -716,8 +728,15 @@ int launch_sliced(apm_plan *pl, SlicedList &l, const uint8_t *d_buf, long long b
 // coordinates), in rounds of 2^27 windows; behind every round the same patterns' ordinary kernels are launched
 // gated on the round's overflow flag (they run only when the candidate buffer was too small).  Stream ordered.
 template <int S>
-void launch_filter_scan(const FilterArgs &a, unsigned blocks, cudaStream_t st) {
-    filter_scan_kernel<S><<<blocks, kFilterThreads, 0, st>>>(a);
+cudaError_t launch_filter_scan(const FilterArgs &a, unsigned blocks, cudaStream_t st, int device) {
+    static std::atomic<bool> attr_set[64];  // 64 KB of dynamic shared memory needs the opt-in once per kernel and device
+    if (device < 0 || device >= 64 || !attr_set[device].load()) {
+        const cudaError_t e = cudaFuncSetAttribute(filter_scan_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFilterSmemBytes + (int)sizeof(FilterStage) * (kFilterThreads / 32));
+        if (e != cudaSuccess) return e;
+        if (device >= 0 && device < 64) attr_set[device].store(true);
+    }
+    filter_scan_kernel<S><<<blocks, kFilterThreads, kFilterSmemBytes + sizeof(FilterStage) * (kFilterThreads / 32), st>>>(a);
+    return cudaGetLastError();
 }
 
 int launch_filter(apm_plan *pl, const uint8_t *d_buf, long long buf_len, long long n_end, long long w0, long long w1,
@@ -735,7 +754,10 @@ int launch_filter(apm_plan *pl, const uint8_t *d_buf, long long buf_len, long lo
     a.mmax = f.mmax;
     a.bs = f.bs;
     a.bitmap = f.d_bitmap;
+    a.digest = f.d_digest;
     a.ent_idx = f.d_ent_idx;
+    a.ent_hash = f.d_ent_hash;
+    a.coarse = f.d_coarse;
     a.ent_slot = f.d_ent_slot;
     a.ent_piece = f.d_ent_piece;
     a.nent = f.nent;
@@ -755,20 +777,22 @@ int launch_filter(apm_plan *pl, const uint8_t *d_buf, long long buf_len, long lo
         CUDA_TRY(cudaMemsetAsync(f.d_ctr, 0, 2 * sizeof(unsigned long long), st));
         const long long positions = a.w1 - a.w0 + f.mmax;
         const long long tiles = (positions + kFilterThreads * kFilterPosPerThread - 1) / (kFilterThreads * kFilterPosPerThread);
-        const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(tiles, (long long)pl->num_sms * 16));
+        // persistent CTAs (3 per SM: 64 KB digest each), every CTA strides over the tiles
+        const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(tiles, (long long)pl->num_sms * 3));
+        cudaError_t le;
         switch (f.s) {
-            case 8: launch_filter_scan<8>(a, blocks, st); break;
-            case 9: launch_filter_scan<9>(a, blocks, st); break;
-            case 10: launch_filter_scan<10>(a, blocks, st); break;
-            case 11: launch_filter_scan<11>(a, blocks, st); break;
-            case 12: launch_filter_scan<12>(a, blocks, st); break;
-            case 13: launch_filter_scan<13>(a, blocks, st); break;
-            case 14: launch_filter_scan<14>(a, blocks, st); break;
-            case 15: launch_filter_scan<15>(a, blocks, st); break;
-            default: launch_filter_scan<16>(a, blocks, st); break;
+            case 8: le = launch_filter_scan<8>(a, blocks, st, pl->device); break;
+            case 9: le = launch_filter_scan<9>(a, blocks, st, pl->device); break;
+            case 10: le = launch_filter_scan<10>(a, blocks, st, pl->device); break;
+            case 11: le = launch_filter_scan<11>(a, blocks, st, pl->device); break;
+            case 12: le = launch_filter_scan<12>(a, blocks, st, pl->device); break;
+            case 13: le = launch_filter_scan<13>(a, blocks, st, pl->device); break;
+            case 14: le = launch_filter_scan<14>(a, blocks, st, pl->device); break;
+            case 15: le = launch_filter_scan<15>(a, blocks, st, pl->device); break;
+            default: le = launch_filter_scan<16>(a, blocks, st, pl->device); break;
         }
-        CUDA_TRY(cudaGetLastError());
-        filter_verify_kernel<<<pl->num_sms * 8, 128, 0, st>>>(a);
+        CUDA_TRY(le);
+        filter_verify_kernel<<<pl->num_sms * 16, 128, 0, st>>>(a);
         CUDA_TRY(cudaGetLastError());
         g_launches += 2;
         int rc;

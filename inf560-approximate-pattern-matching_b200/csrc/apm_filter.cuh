@@ -25,18 +25,14 @@ namespace apm {
 constexpr int kFilterMinSeed = 8;
 constexpr int kFilterMaxSeed = 16;
 constexpr int kFilterMaxK = 16;
-constexpr int kFilterThreads = 128;
+constexpr int kFilterThreads = 256;
 constexpr int kFilterPosPerThread = 16;
 constexpr uint32_t kFilterHashB = 0x9E3779B1u;
-constexpr uint32_t kFilterMixM = 0x2C1B3C6Du;
 constexpr int kFilterSlabLog = 27;  // window starts per scan/verify round: candidates carry a 28-bit local start
 
 // table index of a seed hash (hb bits)
-__host__ __device__ __forceinline__ uint32_t filter_index(uint32_t h, int hb) {
-    h ^= h >> 15;
-    h *= kFilterMixM;
-    return h >> (32 - hb);
-}
+// (the leading bits of the polynomial hash depend on every byte of the seed; no extra mixing step)
+__host__ __device__ __forceinline__ uint32_t filter_index(uint32_t h, int hb) { return h >> (32 - hb); }
 // polynomial hash of s bytes: sum c_i * B^(s-1-i)
 __host__ __device__ inline uint32_t filter_hash(const uint8_t *p, int s) {
     uint32_t h = 0;
@@ -59,6 +55,9 @@ struct FilterArgs {
     int s, k, hb, mmax;
     uint32_t bs;                  // B^s
     const uint32_t *bitmap;       // 2^hb bits
+    const uint32_t *digest;       // 2^19 bits: OR of the bitmap bits with the same leading index bits
+    const uint32_t *coarse;       // [2^16 + 1] first entry of every leading-16-bit class of the table index
+    const uint32_t *ent_hash;     // [nent] full 32-bit hash of every seed (cheap reject before the byte compare)
     const uint32_t *ent_idx;      // [nent] table index of every seed, sorted
     const uint32_t *ent_slot;     // [nent] filtered-pattern slot
     const uint8_t *ent_piece;     // [nent] piece index
@@ -84,15 +83,52 @@ __device__ __forceinline__ uint4 filter_load16(const FilterArgs &a, long long po
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// slow path of the scan: text position t produced table index idx
-__device__ __noinline__ void filter_hit(const FilterArgs &a, long long t, uint32_t idx) {
-    int lo = 0, hi = a.nent;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(a.ent_idx + mid) < idx) lo = mid + 1;
-        else hi = mid;
+// slow path of the scan: text position t has hash h / table index idx and its bit is set in the seed bitmap.
+// The entries are sorted by table index; a coarse directory over the leading 16 index bits gives the (tiny)
+// range to look at in one load.
+// Candidates are staged in a small shared-memory list per WARP and flushed with one global atomic per flush
+// instead of one per candidate (a single contended counter admits ~1 atomic per clock, which bounded the scan).
+constexpr int kFilterStage = 96;
+struct FilterStage {
+    uint64_t item[kFilterStage];
+    unsigned int count;  // may exceed kFilterStage: the excess went straight to global memory
+    unsigned int pad;
+};
+
+__device__ __forceinline__ void filter_emit(const FilterArgs &a, FilterStage *stg, uint64_t packed) {
+    const unsigned int slot = atomicAdd(&stg->count, 1u);
+    if (slot < (unsigned)kFilterStage) {
+        stg->item[slot] = packed;
+    } else {  // staging list full (low-complexity text): append directly
+        const unsigned long long pos = atomicAdd(a.ncand, 1ull);
+        if (pos < a.cap) a.cand[pos] = packed;
+        else *a.overflow = 1u;
     }
-    for (int e = lo; e < a.nent && __ldg(a.ent_idx + e) == idx; ++e) {
+}
+
+// all lanes of the warp (converged): move the warp's staged candidates to the global buffer
+__device__ __forceinline__ void filter_flush(const FilterArgs &a, FilterStage *stg) {
+    __syncwarp();
+    const unsigned int n = min(stg->count, (unsigned)kFilterStage);
+    if (n == 0) return;  // warp-uniform
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(a.ncand, (unsigned long long)n);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    for (unsigned int i = lane; i < n; i += 32) {
+        if (base + i < a.cap) a.cand[base + i] = stg->item[i];
+        else *a.overflow = 1u;
+    }
+    __syncwarp();
+    if (lane == 0) stg->count = 0u;
+    __syncwarp();
+}
+
+__device__ __noinline__ void filter_hit(const FilterArgs &a, FilterStage *stg, long long t, uint32_t idx, uint32_t h) {
+    const uint32_t c = idx >> (a.hb - 16);
+    const int lo = (int)__ldg(a.coarse + c), hi = (int)__ldg(a.coarse + c + 1);
+    for (int e = lo; e < hi; ++e) {
+        if (__ldg(a.ent_idx + e) != idx || __ldg(a.ent_hash + e) != h) continue;
         const uint32_t slot = __ldg(a.ent_slot + e);
         const int piece = __ldg(a.ent_piece + e);
         const int m = __ldg(a.fp_m + slot);
@@ -106,26 +142,57 @@ __device__ __noinline__ void filter_hit(const FilterArgs &a, long long t, uint32
             if (off < 0 || off + a.s > m) continue;
             const long long j = t - off;
             if (j < a.w0 || j >= a.w1 || j + m > a.n_end) continue;  // full windows of this round only
-            const unsigned long long pos = atomicAdd(a.ncand, 1ull);
-            if (pos < a.cap) a.cand[pos] = filter_pack(slot, piece, d + a.k, (uint32_t)(j - a.w0));
-            else *a.overflow = 1u;
+            filter_emit(a, stg, filter_pack(slot, piece, d + a.k, (uint32_t)(j - a.w0)));
         }
     }
 }
 
 // Scan: every text position that can hold a seed of a window of [w0, w1).  A thread owns 16 consecutive
 // positions: its own 16 bytes come from one coalesced 128-bit load, the next 16 from the neighbouring lane by
-// shuffle; rolling hash in registers; the 16 bitmap probes are issued together.
+// shuffle; rolling hash in registers.  Two-level probe: a 64 KB digest of the seed set lives in shared memory
+// (copied once per persistent CTA), so all but ~0.1 % of the positions are rejected by one LDS and only the
+// rest recompute their hash and touch the full bitmap in L2.
+constexpr int kFilterSmemLog = 19;
+constexpr int kFilterSmemBytes = 1 << (kFilterSmemLog - 3);
+
+// slow path of the scan, second level: position t passed the shared-memory digest
+template <int S>
+__device__ __forceinline__ void filter_probe(const FilterArgs &a, FilterStage *stg, long long t) {
+    uint32_t c[S];
+#pragma unroll
+    for (int i = 0; i < S; ++i) c[i] = a.buf[t + i];
+    uint32_t h = 0;
+#pragma unroll
+    for (int i = 0; i < S; ++i) h = h * kFilterHashB + c[i];
+    const uint32_t idx = filter_index(h, a.hb);
+    if ((__ldg(a.bitmap + (idx >> 5)) >> (idx & 31)) & 1u) filter_hit(a, stg, t, idx, h);
+}
+
+// Shared-memory digest: 2^14 words; a seed with hash h sets TWO bits, (h >> 13) & 31 and (h >> 8) & 31, of word
+// h >> 18 (a one-word Bloom filter: one LDS per text position, false-positive rate ~ (bits set per word / 32)^2).
+__host__ __device__ __forceinline__ uint32_t filter_digest_word(uint32_t h) { return h >> 18; }
+__host__ __device__ __forceinline__ uint32_t filter_digest_mask(uint32_t h) {
+    return (1u << ((h >> 13) & 31)) | (1u << ((h >> 8) & 31));
+}
+
 template <int S>
 __global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const FilterArgs a) {
+    extern __shared__ __align__(16) uint32_t s_digest[];
+    FilterStage *stg = reinterpret_cast<FilterStage *>(reinterpret_cast<unsigned char *>(s_digest) + kFilterSmemBytes) +
+                       (threadIdx.x >> 5);  // this warp's staging list
     const long long t_begin = a.w0;
     const long long t_end = min(a.w1 - 1 + a.mmax, a.n_end) - S + 1;  // exclusive
     if (t_end <= t_begin) return;
+    for (int i = threadIdx.x; i < kFilterSmemBytes / 16; i += kFilterThreads)
+        reinterpret_cast<uint4 *>(s_digest)[i] = __ldg(reinterpret_cast<const uint4 *>(a.digest) + i);
+    if ((threadIdx.x & 31) == 0) stg->count = 0u;
+    __syncthreads();
     // align the tile grid to 16-byte addresses of the buffer
     const long long mis = (long long)(reinterpret_cast<uintptr_t>(a.buf + t_begin) & 15);
     const long long base0 = t_begin - mis;
     constexpr long long kTile = (long long)kFilterThreads * kFilterPosPerThread;
     const int lane = threadIdx.x & 31;
+    const unsigned char *dig = reinterpret_cast<const unsigned char *>(s_digest);
     for (long long base = base0 + (long long)blockIdx.x * kTile; base < t_end; base += (long long)gridDim.x * kTile) {
         const long long p0 = base + (long long)threadIdx.x * kFilterPosPerThread;
         const uint4 own = filter_load16(a, p0);
@@ -136,23 +203,33 @@ __global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const Filte
         nxt.w = __shfl_down_sync(0xFFFFFFFFu, own.w, 1);
         if (lane == 31) nxt = filter_load16(a, p0 + 16);
         const uint32_t w[8] = {own.x, own.y, own.z, own.w, nxt.x, nxt.y, nxt.z, nxt.w};
-        auto byte_at = [&](int i) -> uint32_t { return (w[i >> 2] >> (8 * (i & 3))) & 0xFFu; };
+        auto byte_at = [&](int i) -> uint32_t { return __byte_perm(w[i >> 2], 0u, 0x4440 + (i & 3)); };
         uint32_t h = 0;
 #pragma unroll
         for (int i = 0; i < S; ++i) h = h * kFilterHashB + byte_at(i);
-        uint32_t idx[kFilterPosPerThread], word[kFilterPosPerThread];
+        // digest probe of the 16 positions (filter_digest_word / _mask); the answers are shifted into
+        // `maybe` from the top, so position i ends up at bit 16 + i
+        uint32_t maybe = 0u;
 #pragma unroll
         for (int i = 0; i < kFilterPosPerThread; ++i) {
-            idx[i] = filter_index(h, a.hb);
-            word[i] = __ldg(a.bitmap + (idx[i] >> 5));
+            const uint32_t word = *reinterpret_cast<const uint32_t *>(dig + ((h >> 16) & 0xFFFCu));
+            maybe = __funnelshift_r(maybe, __funnelshift_r(word, 0u, h >> 13) & __funnelshift_r(word, 0u, h >> 8), 1);
             if (i + 1 < kFilterPosPerThread) h = h * kFilterHashB - byte_at(i) * a.bs + byte_at(i + S);  // roll by one byte
         }
-#pragma unroll
-        for (int i = 0; i < kFilterPosPerThread; ++i) {
-            const long long t = p0 + i;
-            if (((word[i] >> (idx[i] & 31)) & 1u) && t >= t_begin && t < t_end) filter_hit(a, t, idx[i]);
+        maybe >>= 16;
+        // positions outside [t_begin, t_end) do not count
+        const long long lo = t_begin - p0, hi = t_end - p0;
+        if (lo > 0) maybe &= lo >= 16 ? 0u : ~((1u << (int)lo) - 1u);
+        if (hi < 16) maybe &= hi <= 0 ? 0u : ((1u << (int)hi) - 1u);
+        while (maybe) {  // ~1 % of the positions
+            const int i = __ffs(maybe) - 1;
+            maybe &= maybe - 1u;
+            filter_probe<S>(a, stg, p0 + i);
         }
+        __syncwarp();  // reconverged: flush when the warp's list is a third full (warp-uniform decision)
+        if (stg->count >= (unsigned)kFilterStage / 3) filter_flush(a, stg);
     }
+    filter_flush(a, stg);
 }
 
 // Verify: banded DP of one candidate (cells with |row - col| > k are "infinite"): D[m][m] <= k is decided
