@@ -250,6 +250,7 @@ def run_ours(args) -> None:
     # ---- exact band mode: same slabs, only the 2k+1 diagonals that can matter for D <= k.
     #      Reported separately as EFFECTIVE GCUPS (cells of the reference DP per second, most never touched).
     band = None
+    filt = None
     if not args.no_band:
         apm_b200.set_option("mode", "band")
         bplan = apm_b200.Plan(pats, K_ERR)
@@ -278,6 +279,35 @@ def run_ours(args) -> None:
                 "counts_equal_direct": bool(same),
                 "note": "exact Ukkonen band (9 of 64 diagonals at k=4): (2k+1)*5+(k+1) = 50 LOP3 per row and 32 windows"}
         bplan.close()
+        # ---- exact filter mode (pigeonhole seeds + banded verification): the WHOLE shard of this rank, i.e. the
+        #      complete config-5 job at N ranks, not a slab.  Counts of its first slab must equal the direct kernel's.
+        apm_b200.set_option("mode", "filter")
+        fplan = apm_b200.Plan(pats, K_ERR)
+        fplan.count_device(shard.data_ptr(), b0, b1 - b0, N_TOTAL, j0, j0 + slab, stream)
+        slab_same = fplan.read_counts(stream) == plan.read_counts(stream)
+        fplan.zero_counts(stream)
+        sync_all()
+        f_e0, f_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f_e0.record()
+        fplan.count_device(shard.data_ptr(), b0, b1 - b0, N_TOTAL, j0, j1, stream)
+        if world > 1:
+            reduced.copy_(_tensor_from_ptr(torch, fplan.counts_device_ptr(), NB_PATTERNS, dev))
+            dist.all_reduce(reduced, op=dist.ReduceOp.SUM)
+        f_e1.record()
+        sync_all()
+        fms = f_e0.elapsed_time(f_e1)
+        total_matches = sum(fplan.read_counts(stream))
+        if world > 1:
+            t = torch.tensor([fms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            fms = float(t.item())
+            total_matches = int(reduced.sum().item())
+        filt = {"value": cells_text(N_TOTAL, NB_PATTERNS, M, K_ERR) / (fms * 1e-3) / 1e9, "unit": "effective GCUPS",
+                "full_job_ms": fms, "text_gbs": N_TOTAL / (fms * 1e-3) / 1e9, "total_matches": int(total_matches),
+                "counts_equal_direct_on_slab": bool(slab_same),
+                "note": "complete config-5 job (2^34 B x 4096 patterns, every window start of every rank's shard + "
+                        "count all-reduce) in exact filter mode; the truncated tail windows go through the DP kernel"}
+        fplan.close()
         apm_b200.set_option("mode", "direct")
 
     # ---- end-to-end through the one-shot C-ABI call with HOST buffers ------------------------------
@@ -375,7 +405,7 @@ def run_ours(args) -> None:
                    "kernel": args.kernel, "mode": "direct", "shard": "db", "l2": "successive steps read successive "
                    "slabs of a 16 GiB text (inputs larger than L2)", "text_bytes_per_rank": int(b1 - b0)},
         "text_gbs": text_gbs, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-        "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "parity": parity, "band_mode": band,
+        "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "parity": parity, "band_mode": band, "filter_mode": filt,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

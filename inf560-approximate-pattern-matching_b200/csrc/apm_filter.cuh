@@ -25,7 +25,7 @@ namespace apm {
 constexpr int kFilterMinSeed = 8;
 constexpr int kFilterMaxSeed = 16;
 constexpr int kFilterMaxK = 16;
-constexpr int kFilterThreads = 256;
+constexpr int kFilterThreads = 512;
 constexpr int kFilterPosPerThread = 16;
 constexpr uint32_t kFilterHashB = 0x9E3779B1u;
 constexpr int kFilterSlabLog = 27;  // window starts per scan/verify round: candidates carry a 28-bit local start
@@ -193,9 +193,14 @@ __global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const Filte
     constexpr long long kTile = (long long)kFilterThreads * kFilterPosPerThread;
     const int lane = threadIdx.x & 31;
     const unsigned char *dig = reinterpret_cast<const unsigned char *>(s_digest);
-    for (long long base = base0 + (long long)blockIdx.x * kTile; base < t_end; base += (long long)gridDim.x * kTile) {
+    const long long stride = (long long)gridDim.x * kTile;
+    long long base = base0 + (long long)blockIdx.x * kTile;
+    uint4 pre = make_uint4(0u, 0u, 0u, 0u);  // software prefetch: the next tile's bytes are requested a tile ahead
+    if (base < t_end) pre = filter_load16(a, base + (long long)threadIdx.x * kFilterPosPerThread);
+    for (; base < t_end; base += stride) {
         const long long p0 = base + (long long)threadIdx.x * kFilterPosPerThread;
-        const uint4 own = filter_load16(a, p0);
+        const uint4 own = pre;
+        if (base + stride < t_end) pre = filter_load16(a, p0 + stride);
         uint4 nxt;
         nxt.x = __shfl_down_sync(0xFFFFFFFFu, own.x, 1);
         nxt.y = __shfl_down_sync(0xFFFFFFFFu, own.y, 1);

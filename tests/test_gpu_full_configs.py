@@ -46,6 +46,16 @@ def test_full_config(text_1g, name, P, m, k, submod):
             if offs[p] is not None and nsub[p] <= k:
                 assert whole[p] >= 1, (name, p)
         assert sum(whole) >= sum(1 for p in range(P) if offs[p] is not None and nsub[p] <= k)
+        # (1b) exact filter mode over the whole text gives the same vector
+        apm_b200.set_option("mode", "filter")
+        with apm_b200.Plan(pats, k) as fplan:
+            fplan.count_device(ptr, 0, N, N, 0, W)
+            assert fplan.read_counts() == whole, name
+            fplan.zero_counts()
+            for a, b in ((0, W // 3 + 5), (W // 3 + 5, W)):
+                fplan.count_device(ptr, 0, N, N, a, b)
+            assert fplan.read_counts() == whole, name
+        apm_b200.set_option("mode", "band")
         # (2) 4 database shards (unaligned cuts) add up to the whole
         plan.zero_counts()
         cuts = [0, W // 4 + 3, W // 2 + 17, (3 * W) // 4 + 1, W]
