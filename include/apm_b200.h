@@ -67,8 +67,14 @@ int apm_count_matches_file(const char *path, const char *const *patterns, const 
  *                 row-parallel Hyyro/Myers kernel otherwise (m <= 256), explicit DP for the rest;
  *                 every mode routes the truncated tail windows to the explicit-DP kernel;
  *                 dp: explicit-DP kernel for everything (in-GPU cross-check)
- *   "mode"    = "direct" | "band"     direct (default): every DP cell of every window is evaluated;
- *                                     band: exact Ukkonen band |i-j| <= k (same counts, ~(2k+1)/m of the work)
+ *   "mode"    = "direct" | "band" | "filter"
+ *                 direct (default): every DP cell of every window is evaluated;
+ *                 band: exact Ukkonen band |i-j| <= k (same counts, ~(2k+1)/m of the work);
+ *                 filter: exact pigeonhole filter -- one rolling-hash scan of the text against the seeds of all
+ *                 patterns (k+1 pieces each), banded verification of the candidate windows only; patterns whose
+ *                 pieces are shorter than 8 symbols (or k > 16) and rounds whose candidates overflow the buffer
+ *                 go through the band kernel.  Same counts; work ~ text bytes instead of text bytes x patterns.
+ *   "filter_cand_mb" = candidate buffer of filter mode in MiB (default 128)
  *   "cell"    = "auto" | "lop3" | "fma3" | "fma"   code of one DP cell in the window-sliced / band kernels:
  *                 lop3: 5 LOP3 (ALU pipe only); fma3: 4 LOP3 + 3 IMAD; fma: 4 LOP3 + 2 IMAD (FMA pipe takes the
  *                 subtractions); auto (default) picks per pattern-length class.  Same results, different speed.

@@ -5,8 +5,9 @@
  *   apm <approx_factor> <dna_file> <pattern1> [pattern2 ...] [DB_OVER_RANKS|PATTERNS_OVER_RANKS]
  *
  * The optional trailing flag mirrors src/main.c:66-85 and selects how work is split over GPUs.
- * Extra knobs come from the environment so argv stays drop-in: APM_GPUS, APM_SHARD, APM_KERNEL,
- * APM_RBLOCK, APM_TILE.
+ * Extra knobs come from the environment so argv stays drop-in: APM_GPUS, APM_SHARD, APM_KERNEL, APM_MODE
+ * (direct | band | filter -- all exact), APM_CELL, APM_RBLOCK, APM_TILE; APM_INFO=1 adds the
+ * "(Rank 0) - TOTAL TIME ..." line of the parallel binary (patterns_over_ranks.c:223-226).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -31,7 +32,7 @@ int main(int argc, char **argv) {
     }
     if (set_from_env("APM_GPUS", "gpus") || set_from_env("APM_SHARD", "shard") ||
         set_from_env("APM_KERNEL", "kernel") || set_from_env("APM_RBLOCK", "rblock") ||
-        set_from_env("APM_TILE", "tile"))
+        set_from_env("APM_TILE", "tile") || set_from_env("APM_MODE", "mode") || set_from_env("APM_CELL", "cell"))
         return 1;
 
     /* main.c:66-85: an explicit approach as last argument is consumed, not searched for */
@@ -73,6 +74,11 @@ int main(int argc, char **argv) {
     }
     const double duration = (t2.tv_sec - t1.tv_sec) + ((t2.tv_usec - t1.tv_usec) / 1e6);
     printf("APM done in %lf s\n", duration);
+    if (getenv("APM_INFO") && atoi(getenv("APM_INFO")) > 0) { /* patterns_over_ranks.c:223-226 */
+        const char *omp = getenv("OMP_NUM_THREADS");
+        printf("\n(Rank 0) - TOTAL TIME using %d mpi_ranks and %d omp_thread(s) per rank: %f s\n\n", 1, omp ? atoi(omp) : 0,
+               duration);
+    }
     for (int i = 0; i < nb_patterns; i++)
         printf("Number of matches for pattern <%s>: %lld\n", argv[i + 3], n_matches[i]);
     free(len);
