@@ -59,6 +59,17 @@ int apm_count_matches_file(const char *path, const char *const *patterns, const 
                            int nb_patterns, int approx_factor, long long *n_matches,
                            unsigned long long *n_bytes_out);
 
+/* apm_count_matches that also reports WHERE the matches are (the reference only counts): the
+ * first max_hits matching windows in (pattern index, window start) order go to hit_pattern[] / hit_start[];
+ * *n_hits = number of matching windows found (= sum of n_matches; 0 when max_hits is 0; larger than max_hits when
+ * the arrays were too small -- with several GPUs each device keeps at most max_hits, so the listed hits are then a
+ * subset).
+ * Truncated tail windows are reported with their start like any other window.  n_bytes < 2^40.           */
+int apm_find_matches(const unsigned char *text, size_t n_bytes, const char *const *patterns,
+                     const int *pattern_len, int nb_patterns, int approx_factor, long long *n_matches,
+                     unsigned long long max_hits, int *hit_pattern, unsigned long long *hit_start,
+                     unsigned long long *n_hits);
+
 /* Options (process-wide, read when a call starts):
  *   "gpus"    = "1".."8" | "all"      devices used by the one-shot API (default 1)
  *   "shard"   = "db" | "patterns" | "auto"   how work is split over several GPUs (default auto)
@@ -120,6 +131,12 @@ int apm_plan_count_device(apm_plan *plan, const unsigned char *d_buf,
 /* Restrict the plan to the patterns p with p % world == rank (pattern sharding, mirrors
  * src/patterns_over_ranks.c:161); counters of the other patterns stay 0.  world = 1 resets.      */
 int apm_plan_set_pattern_shard(apm_plan *plan, int rank, int world);
+
+/* Attach (or, with NULLs, detach) a DEVICE array of `capacity` packed hits (pattern index << 40 | global window
+ * start) and a DEVICE counter: every later apm_plan_count_device appends the matching windows it finds
+ * (unordered; the counter keeps counting past the capacity).  The caller zeroes the counter.           */
+int apm_plan_set_hit_buffer(apm_plan *plan, unsigned long long *d_hits, unsigned long long capacity,
+                            unsigned long long *d_n_hits);
 
 int apm_plan_zero_counts(apm_plan *plan, void *stream);
 /* Device pointer to the nb_patterns unsigned 64-bit counters (for an in-place NCCL all-reduce). */

@@ -27,7 +27,7 @@ EXPORTS = [
     "apm_device_count", "apm_set_device", "apm_plan_create", "apm_plan_destroy", "apm_plan_count_device",
     "apm_plan_set_pattern_shard", "apm_plan_zero_counts", "apm_plan_counts_device_ptr",
     "apm_plan_read_counts", "apm_plan_max_pattern_len", "apm_synth_text_device", "apm_int_peak",
-    "apm_launch_count", "apm_version", "apm_release_cache",
+    "apm_launch_count", "apm_version", "apm_release_cache", "apm_find_matches", "apm_plan_set_hit_buffer",
 ]
 
 
@@ -63,6 +63,8 @@ def lib():
     L.apm_plan_count_device.argtypes = [vp, vp, ull, ull, ull, ull, ull, vp]
     L.apm_plan_set_pattern_shard.argtypes = [vp, C.c_int, C.c_int]
     L.apm_plan_zero_counts.argtypes = [vp, vp]
+    L.apm_find_matches.argtypes = [vp, C.c_size_t, vp, vp, C.c_int, C.c_int, vp, ull, vp, vp, vp]
+    L.apm_plan_set_hit_buffer.argtypes = [vp, vp, ull, vp]
     L.apm_plan_counts_device_ptr.argtypes = [vp, vp]
     L.apm_plan_read_counts.argtypes = [vp, vp, vp]
     L.apm_plan_max_pattern_len.argtypes = [vp, vp]
@@ -135,6 +137,21 @@ def count_matches(text, patterns: Sequence[bytes], approx_factor: int) -> list[i
     _check(lib().apm_count_matches(C.addressof(tbuf) if len(tb) else None, len(tb), ptrs, lens, n,
                                    approx_factor, out))
     return [int(out[i]) for i in range(n)]
+
+
+def find_matches(text, patterns: Sequence[bytes], approx_factor: int, max_hits: int = 1 << 20):
+    """-> (n_matches per pattern, [(pattern index, window start), ...] sorted, total number of hits)."""
+    tb = bytes(text) if not isinstance(text, (bytes, bytearray)) else text
+    tbuf = (C.c_ubyte * max(len(tb), 1)).from_buffer_copy(tb if len(tb) else b"\0")
+    bufs, ptrs, lens, n = _pattern_arrays(patterns)
+    out = (C.c_longlong * max(n, 1))()
+    hp = (C.c_int * max(max_hits, 1))()
+    hs = (C.c_ulonglong * max(max_hits, 1))()
+    nh = C.c_ulonglong(0)
+    _check(lib().apm_find_matches(C.addressof(tbuf) if len(tb) else None, len(tb), ptrs, lens, n, approx_factor, out,
+                                  max_hits, hp, hs, C.byref(nh)))
+    k = min(int(nh.value), max_hits)
+    return [int(out[i]) for i in range(n)], [(int(hp[i]), int(hs[i])) for i in range(k)], int(nh.value)
 
 
 def count_matches_ptr(text_ptr: int, n_bytes: int, patterns: Sequence[bytes], approx_factor: int) -> list[int]:

@@ -281,6 +281,7 @@ struct apm_plan {
     unsigned long long *d_counts = nullptr;
     uint32_t *d_scratch = nullptr;
     size_t scratch_bytes = 0;
+    HitSink sink;  // optional match-position output (apm_plan_set_hit_buffer); base is set per call
 };
 
 namespace {
@@ -583,6 +584,7 @@ int launch_myers(apm_plan *pl, Bucket &b, const uint8_t *d_buf, long long buf_le
     a.c_one = 1u;
     a.c_two = 2u;
     a.run_if = run_if;
+    a.sink = pl->sink;
     b.fn<<<dim3(gx, gy), kThreads, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     g_launches++;
@@ -708,6 +710,7 @@ int launch_sliced(apm_plan *pl, SlicedList &l, const uint8_t *d_buf, long long b
     a.lead = 0;
     a.work_counter = nullptr;
     a.run_if = run_if;
+    a.sink = pl->sink;
     a.c_neg1 = 0xFFFFFFFFu;
     // exact band mode: only the 2K+1 diagonals that can matter for D <= k (worth it when the band is
     // narrower than the matrix)
@@ -770,6 +773,7 @@ int launch_filter(apm_plan *pl, const uint8_t *d_buf, long long buf_len, long lo
     a.ncand = f.d_ctr;
     a.overflow = reinterpret_cast<unsigned int *>(f.d_ctr + 1);
     a.counts = pl->d_counts;
+    a.sink = pl->sink;
     const long long round = 1ll << kFilterSlabLog;
     for (long long r0 = w0; r0 < lim; r0 += round) {
         a.w0 = r0;
@@ -818,6 +822,8 @@ int launch_dp(apm_plan *pl, const uint8_t *d_buf, long long buf_offset, long lon
     a.pat_len = pl->d_pat_len;
     a.k = pl->k;
     a.counts = pl->d_counts;
+    a.sink = pl->sink;
+    a.sink.base = 0;  // the DP kernels work on global window starts
 
     // ---- truncated tail windows of the bit-parallel patterns
     if (!pl->tail_list.empty() && pl->tail_width > 0) {
@@ -1120,6 +1126,18 @@ int apm_plan_set_pattern_shard(apm_plan *pl, int rank, int world) {
     return build_work(pl);
 }
 
+int apm_plan_set_hit_buffer(apm_plan *pl, unsigned long long *d_hits, unsigned long long capacity,
+                            unsigned long long *d_n_hits) {
+    if (!pl) return fail(APM_EINVAL, "plan is NULL");
+    if ((d_hits == nullptr) != (d_n_hits == nullptr) || (d_hits && capacity == 0))
+        return fail(APM_EINVAL, "hit buffer, its capacity and its counter go together");
+    if (pl->P >= (1 << (64 - kHitPosBits))) return fail(APM_EINVAL, "too many patterns for packed hit entries");
+    pl->sink.buf = d_hits;
+    pl->sink.cap = d_hits ? capacity : 0;
+    pl->sink.count = d_n_hits;
+    return APM_OK;
+}
+
 int apm_plan_zero_counts(apm_plan *pl, void *stream) {
     if (!pl) return fail(APM_EINVAL, "plan is NULL");
     CUDA_TRY(cudaMemsetAsync(pl->d_counts, 0, sizeof(unsigned long long) * std::max(1, pl->P), (cudaStream_t)stream));
@@ -1169,6 +1187,7 @@ int apm_plan_count_device(apm_plan *pl, const unsigned char *d_buf, unsigned lon
     int cur = -1;
     CUDA_TRY(cudaGetDevice(&cur));
     if (cur != pl->device) CUDA_TRY(cudaSetDevice(pl->device));
+    pl->sink.base = (long long)buf_offset;  // the bit-parallel kernels work on buffer-local window starts
     int rc = APM_OK;
     for (auto &b : pl->buckets) {
         rc = launch_myers(pl, b, d_buf, (long long)buf_len, N - (long long)buf_offset, jb - (long long)buf_offset,
@@ -1311,6 +1330,7 @@ struct DevJob {
     cudaStream_t st = nullptr, copy_st = nullptr;  // count kernels / H2D copies of the file ingest
     apm_plan *plan = nullptr;
     uint8_t *d_text = nullptr;
+    unsigned long long *d_hits = nullptr;  // [0] counter, [1..] packed hits (apm_find_matches)
     long long j0 = 0, j1 = 0, b0 = 0, b1 = 0;  // window-start range and byte range (global)
 };
 
@@ -1320,6 +1340,7 @@ void release_jobs(std::vector<DevJob> &jobs, int restore_dev) {
         if (j.st) cudaStreamSynchronize(j.st);
         if (j.plan) apm_plan_destroy(j.plan);
         if (j.d_text) dev_free(j.d_text);
+        if (j.d_hits) dev_free(j.d_hits);
         if (j.st) cudaStreamDestroy(j.st);
         if (j.copy_st) cudaStreamDestroy(j.copy_st);
     }
@@ -1388,8 +1409,16 @@ int copy_range_to_device(const TextSource &src, long long b0, long long b1, uint
     return rc;
 }
 
+// optional match positions of the one-shot API
+struct HitRequest {
+    unsigned long long max_hits = 0;
+    int *hit_pattern = nullptr;
+    unsigned long long *hit_start = nullptr;
+    unsigned long long n_hits = 0;  // out: all matching windows, may exceed max_hits
+};
+
 int count_impl(const TextSource &src, long long N, const char *const *patterns, const int *pattern_len,
-               int nb_patterns, int approx_factor, long long *n_matches) {
+               int nb_patterns, int approx_factor, long long *n_matches, HitRequest *hits = nullptr) {
     int rc = check_patterns(patterns, pattern_len, nb_patterns, approx_factor);
     if (rc) return rc;
     if (nb_patterns > 0 && !n_matches) return fail(APM_EINVAL, "n_matches is NULL");
@@ -1439,6 +1468,13 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
         mark("stream create", nullptr);
         if ((rc = apm_plan_create(patterns, pattern_len, nb_patterns, approx_factor, &j.plan))) return bail(rc);
         mark("plan create", nullptr);
+        if (hits && hits->max_hits > 0) {  // every GPU may find up to max_hits positions
+            if (dev_alloc((void **)&j.d_hits, (hits->max_hits + 1) * sizeof(unsigned long long)) != cudaSuccess)
+                return bail(fail(APM_ENOMEM, "cudaMalloc of the hit buffer (%llu entries) failed", hits->max_hits));
+            if (cudaMemsetAsync(j.d_hits, 0, sizeof(unsigned long long), j.st) != cudaSuccess)
+                return bail(fail(APM_ECUDA, "cudaMemsetAsync failed"));
+            if ((rc = apm_plan_set_hit_buffer(j.plan, j.d_hits + 1, hits->max_hits, j.d_hits))) return bail(rc);
+        }
         if (shard == SHARD_PATTERNS) {
             if (G > 1 && (rc = apm_plan_set_pattern_shard(j.plan, g, G))) return bail(rc);
             j.j0 = 0;
@@ -1510,6 +1546,31 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
         if ((rc = apm_plan_read_counts(jobs[g].plan, part.data(), jobs[g].st))) return bail(rc);
         for (int i = 0; i < nb_patterns; ++i) n_matches[i] += part[i];
     }
+    if (hits && hits->max_hits > 0) {  // gather, order by (pattern, start), keep the first max_hits
+        std::vector<unsigned long long> all;
+        hits->n_hits = 0;
+        for (int g = 0; g < G; ++g) {
+            cudaSetDevice(jobs[g].dev);
+            unsigned long long n = 0;
+            if (cudaMemcpyAsync(&n, jobs[g].d_hits, sizeof n, cudaMemcpyDeviceToHost, jobs[g].st) != cudaSuccess ||
+                cudaStreamSynchronize(jobs[g].st) != cudaSuccess)
+                return bail(fail(APM_ECUDA, "reading the hit counter failed on device %d", jobs[g].dev));
+            hits->n_hits += n;
+            const unsigned long long take = std::min(n, hits->max_hits);
+            const size_t old = all.size();
+            all.resize(old + take);
+            if (take && (cudaMemcpyAsync(all.data() + old, jobs[g].d_hits + 1, take * sizeof(unsigned long long),
+                                         cudaMemcpyDeviceToHost, jobs[g].st) != cudaSuccess ||
+                         cudaStreamSynchronize(jobs[g].st) != cudaSuccess))
+                return bail(fail(APM_ECUDA, "reading the hits failed on device %d", jobs[g].dev));
+        }
+        std::sort(all.begin(), all.end());  // packed as pattern << 40 | start
+        const size_t keep = (size_t)std::min<unsigned long long>(all.size(), hits->max_hits);
+        for (size_t i = 0; i < keep; ++i) {
+            hits->hit_pattern[i] = (int)(all[i] >> kHitPosBits);
+            hits->hit_start[i] = all[i] & ((1ull << kHitPosBits) - 1);
+        }
+    }
     mark("reduce + D2H", nullptr);
     release_jobs(jobs, restore);
     mark("release", nullptr);
@@ -1525,6 +1586,24 @@ int apm_count_matches(const unsigned char *text, size_t n_bytes, const char *con
     static const unsigned char empty = 0;
     src.host = text ? text : &empty;
     return count_impl(src, (long long)n_bytes, patterns, pattern_len, nb_patterns, approx_factor, n_matches);
+}
+
+int apm_find_matches(const unsigned char *text, size_t n_bytes, const char *const *patterns, const int *pattern_len,
+                     int nb_patterns, int approx_factor, long long *n_matches, unsigned long long max_hits,
+                     int *hit_pattern, unsigned long long *hit_start, unsigned long long *n_hits) {
+    if (!text && n_bytes > 0) return fail(APM_EINVAL, "text is NULL");
+    if (max_hits > 0 && (!hit_pattern || !hit_start)) return fail(APM_EINVAL, "hit arrays are NULL");
+    if (n_bytes >= (1ull << kHitPosBits)) return fail(APM_EINVAL, "text too large for packed hit entries");
+    TextSource src;
+    static const unsigned char empty = 0;
+    src.host = text ? text : &empty;
+    HitRequest hr;
+    hr.max_hits = max_hits;
+    hr.hit_pattern = hit_pattern;
+    hr.hit_start = hit_start;
+    const int rc = count_impl(src, (long long)n_bytes, patterns, pattern_len, nb_patterns, approx_factor, n_matches, &hr);
+    if (n_hits) *n_hits = hr.n_hits;
+    return rc;
 }
 
 int apm_count_matches_file(const char *path, const char *const *patterns, const int *pattern_len,

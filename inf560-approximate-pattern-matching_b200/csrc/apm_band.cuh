@@ -147,7 +147,9 @@ __global__ void __launch_bounds__(kSlicedThreads, 3) band_count_kernel(const Sli
                     T[0] |= z;
                 }
                 // D[m][m] <= k  <=>  not (count > k)
-                hits = __popc(~T[K] & validmask);
+                const uint32_t hitmask = ~T[K] & validmask;
+                hits = __popc(hitmask);
+                if (a.sink.buf && hitmask) hit_emit_mask(a.sink, __ldg(a.pat_id + pi), jbase, hitmask);
             }
             hits = __reduce_add_sync(0xFFFFFFFFu, hits);
             if ((tid & 31) == 0 && hits) atomicAdd(&a.counts[__ldg(a.pat_id + pi)], (unsigned long long)hits);

@@ -23,7 +23,30 @@ __host__ __device__ constexpr int entry_words(int rnw) {
     return rnw >= 4 ? ((rnw + 3) / 4) * 4 : (rnw >= 2 ? 2 : 1);
 }
 
+// Optional output of the match POSITIONS (apm_find_matches / apm_plan_set_hit_buffer): every kernel that counts a
+// matching window also appends (pattern index << 40 | global window start) when a sink is attached.
+struct HitSink {
+    unsigned long long *buf = nullptr;    // device array of `cap` entries, or nullptr (positions not wanted)
+    unsigned long long cap = 0;
+    unsigned long long *count = nullptr;  // device counter: total hits, may exceed cap
+    long long base = 0;                   // global index of local window start 0
+};
+constexpr int kHitPosBits = 40;
+
 #ifdef __CUDACC__
+__device__ __forceinline__ void hit_emit(const HitSink &h, int pattern, long long local_start) {
+    const unsigned long long pos = atomicAdd(h.count, 1ull);
+    if (pos < h.cap) h.buf[pos] = ((unsigned long long)pattern << kHitPosBits) | (unsigned long long)(h.base + local_start);
+}
+// all set bits of a 32-window hit mask whose bit 0 is local window start j0
+__device__ __forceinline__ void hit_emit_mask(const HitSink &h, int pattern, long long j0, uint32_t mask) {
+    while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        hit_emit(h, pattern, j0 + b);
+    }
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -31,6 +31,7 @@ struct DpArgs {
     uint32_t *scratch;            // [(mmax+1)][scratch_stride]
     long long scratch_stride;     // = total threads of the launch
     unsigned long long *counts;
+    HitSink sink;                 // optional match-position output (window starts are global here: base = 0)
 };
 
 // Distance of pattern[0..size) vs text window [j, j+size): the DP of utils.c:76-99 with the column
@@ -74,7 +75,10 @@ __global__ void __launch_bounds__(128) dp_tail_kernel(const DpArgs a) {
     const int size = left < m ? (int)left : m;
     const uint32_t d = dp_window(a.pat_bytes + a.pat_off[p], a.buf + (j - a.buf_offset), size,
                                  a.scratch + gtid, a.scratch_stride);
-    if (d <= (uint32_t)a.k) atomicAdd(&a.counts[p], 1ull);
+    if (d <= (uint32_t)a.k) {
+        atomicAdd(&a.counts[p], 1ull);
+        if (a.sink.buf) hit_emit(a.sink, p, j);
+    }
 }
 
 // All-windows mode: blockIdx.y = pattern slot, grid-stride over window starts [j_begin, j_end).
@@ -91,6 +95,7 @@ __global__ void __launch_bounds__(128) dp_all_kernel(const DpArgs a) {
         const int size = left < m ? (int)left : m;
         const uint32_t d = dp_window(pat, a.buf + (j - a.buf_offset), size, col, a.scratch_stride);
         hits += (d <= (uint32_t)a.k);
+        if (a.sink.buf && d <= (uint32_t)a.k) hit_emit(a.sink, p, j);
     }
     // warp-aggregate (all lanes of a warp share the pattern)
     for (int o = 16; o > 0; o >>= 1) hits += __shfl_down_sync(0xFFFFFFFFu, hits, o);

@@ -71,6 +71,7 @@ struct FilterArgs {
     unsigned long long *ncand;    // zeroed before the scan
     unsigned int *overflow;       // zeroed before the scan; set when cand is full
     unsigned long long *counts;
+    HitSink sink;                 // optional match-position output
 };
 
 __device__ __forceinline__ uint4 filter_load16(const FilterArgs &a, long long pos) {
@@ -289,7 +290,10 @@ __global__ void __launch_bounds__(128) filter_verify_kernel(const FilterArgs a) 
                 if (same) canonical = false;
             }
         }
-        if (canonical) atomicAdd(&a.counts[__ldg(a.fp_id + slot)], 1ull);
+        if (canonical) {
+            atomicAdd(&a.counts[__ldg(a.fp_id + slot)], 1ull);
+            if (a.sink.buf) hit_emit(a.sink, __ldg(a.fp_id + slot), j);
+        }
     }
 }
 

@@ -7,7 +7,8 @@
  * The optional trailing flag mirrors src/main.c:66-85 and selects how work is split over GPUs.
  * Extra knobs come from the environment so argv stays drop-in: APM_GPUS, APM_SHARD, APM_KERNEL, APM_MODE
  * (direct | band | filter -- all exact), APM_CELL, APM_RBLOCK, APM_TILE; APM_INFO=1 adds the
- * "(Rank 0) - TOTAL TIME ..." line of the parallel binary (patterns_over_ranks.c:223-226).
+ * "(Rank 0) - TOTAL TIME ..." line of the parallel binary (patterns_over_ranks.c:223-226); APM_POSITIONS=n
+ * additionally lists the first n matches as "Match of pattern <p> at byte j" (not in the reference).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -63,11 +64,39 @@ int main(int argc, char **argv) {
            nb_patterns, filename, approx_factor); /* sic -- sequential.c:79-82 */
 
     struct timeval t1, t2;
-    gettimeofday(&t1, NULL);
     unsigned long long n_bytes = 0;
-    const int rc = apm_count_matches_file(filename, (const char *const *)(argv + 3), len, nb_patterns,
-                                          approx_factor, n_matches, &n_bytes);
-    gettimeofday(&t2, NULL);
+    const long long want_pos = getenv("APM_POSITIONS") ? atoll(getenv("APM_POSITIONS")) : 0;
+    int *hit_pattern = NULL;
+    unsigned long long *hit_start = NULL, n_hits = 0;
+    int rc;
+    if (want_pos > 0) { /* positions need the text in host memory: read it as utils.c:12-68 does, with 64-bit sizes */
+        FILE *fp = fopen(filename, "rb");
+        unsigned char *buf = NULL;
+        if (fp && fseek(fp, 0, SEEK_END) == 0) {
+            const long sz = ftell(fp);
+            rewind(fp);
+            buf = (unsigned char *)malloc(sz > 0 ? (size_t)sz : 1);
+            if (buf && sz >= 0 && fread(buf, 1, (size_t)sz, fp) == (size_t)sz) n_bytes = (unsigned long long)sz;
+            else { free(buf); buf = NULL; }
+        }
+        if (fp) fclose(fp);
+        if (!buf) {
+            fprintf(stderr, "Unable to open the text file <%s>\n", filename);
+            return 1;
+        }
+        hit_pattern = (int *)malloc(sizeof(int) * (size_t)want_pos);
+        hit_start = (unsigned long long *)malloc(sizeof(unsigned long long) * (size_t)want_pos);
+        gettimeofday(&t1, NULL);
+        rc = apm_find_matches(buf, (size_t)n_bytes, (const char *const *)(argv + 3), len, nb_patterns, approx_factor,
+                              n_matches, (unsigned long long)want_pos, hit_pattern, hit_start, &n_hits);
+        gettimeofday(&t2, NULL);
+        free(buf);
+    } else {
+        gettimeofday(&t1, NULL);
+        rc = apm_count_matches_file(filename, (const char *const *)(argv + 3), len, nb_patterns, approx_factor, n_matches,
+                                    &n_bytes);
+        gettimeofday(&t2, NULL);
+    }
     if (rc != APM_OK) {
         fprintf(stderr, "%s\n", apm_last_error());
         return 1;
@@ -81,6 +110,10 @@ int main(int argc, char **argv) {
     }
     for (int i = 0; i < nb_patterns; i++)
         printf("Number of matches for pattern <%s>: %lld\n", argv[i + 3], n_matches[i]);
+    for (unsigned long long h = 0; h < n_hits && h < (unsigned long long)want_pos; h++)
+        printf("Match of pattern <%s> at byte %llu\n", argv[hit_pattern[h] + 3], hit_start[h]);
+    free(hit_pattern);
+    free(hit_start);
     free(len);
     free(n_matches);
     return 0;

@@ -241,6 +241,7 @@ struct MyersArgs {
     int tile;                    // window starts per tile (multiple of kThreads)
     uint32_t c_one, c_two;       // the constants 1 and 2, opaque to ptxas (see myers_step_fma)
     const unsigned int *run_if;  // optional gate: the whole launch is a no-op when *run_if == 0 (filter fallback)
+    HitSink sink;                // optional match-position output
 };
 
 // Shared-memory layout (dynamic): see myers_smem_bytes() -- the host uses the same formula.
@@ -426,6 +427,7 @@ __global__ void __launch_bounds__(kThreads) myers_count_kernel(const MyersArgs a
                     for (int r = 0; r < R; ++r) {
                         const bool hit = valid && (myers_score_minus_len<NW>(Pv[r], Mv[r], topmask) <= thresh);
                         cnt[r] += __popc(__ballot_sync(0xFFFFFFFFu, hit));
+                        if (a.sink.buf && hit && s_gpat[g * R + r] >= 0) hit_emit(a.sink, s_gpat[g * R + r], ts + woff);
                     }
                 }
                 if (lane == 0) {

@@ -74,6 +74,7 @@ struct SlicedArgs {
     int row_cols;                // 32-bit windows stored per U row (32; 32 + 2K for the band kernel)
     int lead;                    // text positions staged BEFORE the tile start (0; 32 for the band kernel)
     unsigned long long *work_counter;  // zeroed before the launch: dynamic (tile, range) item dispenser
+    HitSink sink;                // optional match-position output
     const unsigned int *run_if;  // optional gate: the whole launch is a no-op when *run_if == 0 (filter fallback)
     uint32_t c_neg1;             // the constant 0xFFFFFFFF, opaque to ptxas (multiplier of the FMA-pipe subtractions)
 };
@@ -448,7 +449,9 @@ __global__ void __launch_bounds__(kSlicedThreads, MC == 64 ? 3 : 4) sliced_count
                     lt |= eqm & ~tot[l] & tb;
                     eqm &= ~(tot[l] ^ tb);
                 }
-                hits = __popc((lt | eqm) & validmask);
+                const uint32_t hitmask = (lt | eqm) & validmask;
+                hits = __popc(hitmask);
+                if (a.sink.buf && hitmask) hit_emit_mask(a.sink, __ldg(a.pat_id + pi), jbase, hitmask);
             }
             hits = __reduce_add_sync(0xFFFFFFFFu, hits);
             if ((tid & 31) == 0 && hits) atomicAdd(&a.counts[__ldg(a.pat_id + pi)], (unsigned long long)hits);

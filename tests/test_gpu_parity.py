@@ -664,3 +664,41 @@ def test_file_ingest_pipeline_multi_chunk(tmp_path, mode):
     want = apm_b200.count_matches(text, pats, k)
     assert all(w >= 1 for w in want)
     assert apm_b200.count_matches_file(str(f), pats, k) == want
+
+
+# ---------------------------------------------------------------------------------------------
+# match positions: every kernel reports WHERE it counted
+# ---------------------------------------------------------------------------------------------
+def _oracle_positions(text, pats, k):
+    out = []
+    for p, pat in enumerate(pats):
+        d = oracle.distances(text, pat, k)
+        out += [(p, int(j)) for j in np.nonzero(d <= k)[0]]
+    return out
+
+
+@pytest.mark.parametrize("mode,kernel", [("direct", "auto"), ("band", "auto"), ("filter", "auto"), ("direct", "myers"),
+                                         ("direct", "dp")])
+def test_find_matches_positions(mode, kernel):
+    """(pattern, window start) of every match, incl. shifted neighbours of planted copies and truncated tail windows."""
+    rng = np.random.default_rng(31)
+    text, pats = _edited_copies_case(rng, 90_000, [64, 40, 100, 33, 200], 3)
+    pats.append(text[-30:] + b"ACGTACGTAC")  # prefix == text suffix: truncated tail windows match
+    k = 3
+    apm_b200.set_option("mode", mode)
+    apm_b200.set_option("kernel", kernel)
+    counts, hits, n_hits = apm_b200.find_matches(text, pats, k)
+    want = _oracle_positions(text, pats, k)
+    assert counts == oracle.count_matches(text, pats, k)
+    assert n_hits == len(want) == sum(counts)
+    assert hits == want
+    assert any(j > len(text) - 40 for p, j in hits if p == len(pats) - 1)
+
+
+def test_find_matches_capacity_and_golden():
+    case = next(c for c in CASES if c["name"] == "x100_k2")
+    counts, hits, n_hits = apm_b200.find_matches(FX[case["text"]], case["patterns"], case["k"], max_hits=50)
+    assert counts == case["expected"] and n_hits == sum(case["expected"]) and len(hits) == 50
+    assert hits == sorted(hits)
+    counts, hits, n_hits = apm_b200.find_matches(FX[case["text"]], case["patterns"], case["k"], max_hits=0)
+    assert counts == case["expected"] and hits == [] and n_hits == 0
