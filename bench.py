@@ -359,7 +359,7 @@ def run_ours(args) -> None:
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            tr = json.load(f).get("sliced_count_kernel<64>", {})
+            tr = json.load(f).get("sliced_count_kernel<64, 1>", {})
         if args.kernel in ("auto", "sliced") and tr.get("slab_windows") == slab and tr.get("patterns") == NB_PATTERNS:
             traffic = tr["dram_bytes_per_launch"]
     except Exception:
@@ -368,12 +368,14 @@ def run_ours(args) -> None:
     roofline = {
         "bound": "int_alu", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tiop/s",
         "frac": achieved / int_peak, "traffic": traffic, "algorithmic_bytes": algorithmic_bytes,
-        "kernel": "sliced_count_kernel<64>" if args.kernel in ("auto", "sliced") else "myers_count_kernel<2,4,0>",
+        "kernel": "sliced_count_kernel<64, 1>" if args.kernel in ("auto", "sliced") else "myers_count_kernel<2,4,0>",
         "algorithmic_ops_per_unit": "10*m*ceil(m/32) = 1280 int32 ops per (pattern, window), SURVEY.md 8d",
         "peak_source": "measured in this run: max(LOP3+IADD3, LOP3+IMAD) dependency-free microbenchmark",
         "lop3_only_peak": peak1 / 1e12,
-        "note": "the boolean work can only issue on the ALU pipe (LOP3-only peak); the sliced kernel executes "
-                "5*m*m/32 = 640 LOP3 per unit, the row-parallel Myers kernel ~1170 ALU-pipe instructions",
+        "note": "frac is on SURVEY's ALGORITHMIC op count (10 ops per 32-cell word step of the row-parallel "
+                "formulation). The window-sliced kernel EXECUTES fewer: 4 LOP3 (ALU pipe) + 3 IMAD (FMA pipe) per "
+                "cell and 32 windows = 512 + 384 instructions per unit, so frac can exceed 1; its own bounds are "
+                "the ALU pipe (lop3_only_peak; ncu: 81 % busy) and register-file operand bandwidth (DESIGN.md 4.1)",
     }
     roofline_hbm = {"bound": "hbm", "achieved": text_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": text_gbs / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
