@@ -159,7 +159,7 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -409,7 +409,7 @@ def run_ours(args) -> None:
         "text_gbs": text_gbs, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "parity": parity, "band_mode": band, "filter_mode": filt,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -421,6 +421,29 @@ def _tensor_from_ptr(torch, ptr: int, n: int, dev):
         __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
 
     return torch.as_tensor(_Holder(), device=dev)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout() -> None:
+    """Library chatter (e.g. "NCCL version ..." printed by NCCL on fd 1) must not precede the ONE JSON line: from
+    here on fd 1 points at stderr, and _emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
 
 
 def main() -> None:
@@ -438,6 +461,7 @@ def main() -> None:
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -13,7 +13,8 @@ FX = fixtures()
 ok = True
 for name in ("easy_k2", "small_k2", "small_k25", "small_m200_k10"):
     c = next(c for c in cases() if c["name"] == name)
-    for kernel, mode in (("auto", "direct"), ("auto", "band"), ("myers", "direct"), ("dp", "direct")):
+    for kernel, mode in (("auto", "direct"), ("auto", "band"), ("auto", "filter"), ("myers", "direct"), ("myers", "filter"),
+                         ("dp", "direct")):
         apm_b200.set_option("kernel", kernel); apm_b200.set_option("mode", mode)
         got = apm_b200.count_matches(FX[c["text"]], c["patterns"], c["k"])
         ok &= got == c["expected"]
@@ -22,8 +23,17 @@ apm_b200.set_option("kernel", "auto")
 text = oracle.synth_text(0x5EED0001, 5, 20000).tobytes()
 pats = [text[100:164], text[3000:3300], text[9000:9033], text[-20:] + b"ACGTAC"]
 want = oracle.count_matches(text, pats, 3)
-for mode in ("direct", "band"):
+for cell in ("lop3", "fma3", "fma"):
+    apm_b200.set_option("cell", cell)
+    got = apm_b200.count_matches(text, pats, 3)
+    ok &= got == want
+    print("cell", cell, "ok" if got == want else f"MISMATCH {got} {want}")
+apm_b200.set_option("cell", "auto")
+for mode in ("direct", "band", "filter"):
     apm_b200.set_option("mode", mode)
+    counts, hits, n_hits = apm_b200.find_matches(text, pats, 3, max_hits=64)
+    ok &= counts == want and n_hits == sum(want)
+    print("positions", mode, "ok" if counts == want and n_hits == sum(want) else f"MISMATCH {counts} {n_hits}")
     dev = torch.zeros(len(text) + 64, dtype=torch.uint8, device="cuda")
     dev[7:7 + len(text)].copy_(torch.frombuffer(bytearray(text), dtype=torch.uint8))
     with apm_b200.Plan(pats, 3) as plan:
@@ -32,5 +42,23 @@ for mode in ("direct", "band"):
         got = plan.read_counts()
     ok &= got == want
     print("shards", mode, "ok" if got == want else f"MISMATCH {got} {want}")
+# filter mode with an overflowing candidate buffer (fallback to the band kernel) on low-complexity text
+apm_b200.set_option("mode", "filter"); apm_b200.set_option("filter_cand_mb", "1")
+lc = b"A" * 200000
+got = apm_b200.count_matches(lc, [b"A" * 40, b"A" * 20 + b"C" + b"A" * 19], 2)
+apm_b200.set_option("mode", "band")
+want_lc = apm_b200.count_matches(lc, [b"A" * 40, b"A" * 20 + b"C" + b"A" * 19], 2)
+ok &= got == want_lc
+print("filter overflow", "ok" if got == want_lc else f"MISMATCH {got} {want_lc}")
+apm_b200.set_option("filter_cand_mb", "128"); apm_b200.set_option("mode", "direct")
+# the reference's entry points by name
+from apm_b200 import refcompat
+r = refcompat.invoke_and_fetch(text, pats[0], 3, initial=2)
+ok &= r == want[0] + 2
+print("refcompat invoke_kernel", "ok" if r == want[0] + 2 else f"MISMATCH {r}")
+r = refcompat.initialize_and_fetch(text, pats, 3, 10000, 1, 3, 0, 3)
+w = [oracle.count_range(text[:10000 + len(p) - 1], p, 3, 0, 10000 + len(p) - 1) for p in pats[:3]] + [0]
+ok &= r == w
+print("refcompat initializeGPU", "ok" if r == w else f"MISMATCH {r} {w}")
 print("ALL OK" if ok else "FAILURES")
 sys.exit(0 if ok else 1)
