@@ -6,7 +6,7 @@
  *
  * The optional trailing flag mirrors src/main.c:66-85 and selects how work is split over GPUs.
  * Extra knobs come from the environment so argv stays drop-in: APM_GPUS, APM_SHARD, APM_KERNEL, APM_MODE
- * (direct | band | filter -- all exact), APM_CELL, APM_RBLOCK, APM_TILE; APM_INFO=1 adds the
+ * (direct | band | filter -- all exact, same counts; the CLI defaults to filter), APM_CELL, APM_RBLOCK, APM_TILE; APM_INFO=1 adds the
  * "(Rank 0) - TOTAL TIME ..." line of the parallel binary (patterns_over_ranks.c:223-226); APM_POSITIONS=n
  * additionally lists the first n matches as "Match of pattern <p> at byte j" (not in the reference).
  */
@@ -31,6 +31,8 @@ int main(int argc, char **argv) {
         printf("Usage: %s approximation_factor dna_database pattern1 pattern2 ...\n", argv[0]);
         return 1;
     }
+    /* every mode is exact; the CLI defaults to the fastest one (the library default is "direct": every DP cell) */
+    apm_set_option("mode", "filter");
     if (set_from_env("APM_GPUS", "gpus") || set_from_env("APM_SHARD", "shard") ||
         set_from_env("APM_KERNEL", "kernel") || set_from_env("APM_RBLOCK", "rblock") ||
         set_from_env("APM_TILE", "tile") || set_from_env("APM_MODE", "mode") || set_from_env("APM_CELL", "cell"))
