@@ -90,10 +90,12 @@ __device__ __forceinline__ uint4 filter_load16(const FilterArgs &a, long long po
 // Candidates are staged in a small shared-memory list per WARP and flushed with one global atomic per flush
 // instead of one per candidate (a single contended counter admits ~1 atomic per clock, which bounded the scan).
 constexpr int kFilterStage = 96;
+constexpr int kFilterQueue = 64;
 struct FilterStage {
     uint64_t item[kFilterStage];
-    unsigned int count;  // may exceed kFilterStage: the excess went straight to global memory
-    unsigned int pad;
+    unsigned int count;   // may exceed kFilterStage: the excess went straight to global memory
+    unsigned int qcount;  // text positions that passed the digest and wait for the second-level probe
+    uint32_t queue[kFilterQueue];  // ... as offsets from the first scanned position of the round
 };
 
 __device__ __forceinline__ void filter_emit(const FilterArgs &a, FilterStage *stg, uint64_t packed) {
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const Filte
     if (t_end <= t_begin) return;
     for (int i = threadIdx.x; i < kFilterSmemBytes / 16; i += kFilterThreads)
         reinterpret_cast<uint4 *>(s_digest)[i] = __ldg(reinterpret_cast<const uint4 *>(a.digest) + i);
-    if ((threadIdx.x & 31) == 0) stg->count = 0u;
+    if ((threadIdx.x & 31) == 0) { stg->count = 0u; stg->qcount = 0u; }
     __syncthreads();
     // align the tile grid to 16-byte addresses of the buffer
     const long long mis = (long long)(reinterpret_cast<uintptr_t>(a.buf + t_begin) & 15);
@@ -227,13 +229,29 @@ __global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const Filte
         const long long lo = t_begin - p0, hi = t_end - p0;
         if (lo > 0) maybe &= lo >= 16 ? 0u : ~((1u << (int)lo) - 1u);
         if (hi < 16) maybe &= hi <= 0 ? 0u : ((1u << (int)hi) - 1u);
-        while (maybe) {  // ~1 % of the positions
+        // ~0.1 % of the positions pass the digest.  They are queued per warp and probed 32 at a time with all
+        // lanes busy (probing inline would stall the whole warp behind one lane's dependent loads).
+        while (maybe) {
             const int i = __ffs(maybe) - 1;
             maybe &= maybe - 1u;
-            filter_probe<S>(a, stg, p0 + i);
+            const unsigned int slot = atomicAdd(&stg->qcount, 1u);
+            if (slot < (unsigned)kFilterQueue) stg->queue[slot] = (uint32_t)(p0 + i - base0);
+            else filter_probe<S>(a, stg, p0 + i);  // queue full: probe right away
         }
-        __syncwarp();  // reconverged: flush when the warp's list is a third full (warp-uniform decision)
+        __syncwarp();
+        if (stg->qcount >= 32u) {  // warp-uniform
+            const unsigned int n = min(stg->qcount, (unsigned)kFilterQueue);
+            for (unsigned int q = lane; q < n; q += 32) filter_probe<S>(a, stg, base0 + stg->queue[q]);
+            __syncwarp();
+            if (lane == 0) stg->qcount = 0u;
+            __syncwarp();
+        }
         if (stg->count >= (unsigned)kFilterStage / 3) filter_flush(a, stg);
+    }
+    __syncwarp();
+    {
+        const unsigned int n = min(stg->qcount, (unsigned)kFilterQueue);
+        for (unsigned int q = lane; q < n; q += 32) filter_probe<S>(a, stg, base0 + stg->queue[q]);
     }
     filter_flush(a, stg);
 }
