@@ -179,7 +179,7 @@ __host__ __device__ __forceinline__ uint32_t filter_digest_mask(uint32_t h) {
 }
 
 template <int S>
-__global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const FilterArgs a) {
+__global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const __grid_constant__ FilterArgs a) {
     extern __shared__ __align__(16) uint32_t s_digest[];
     FilterStage *stg = reinterpret_cast<FilterStage *>(reinterpret_cast<unsigned char *>(s_digest) + kFilterSmemBytes) +
                        (threadIdx.x >> 5);  // this warp's staging list
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const Filte
 
 // Verify: banded DP of one candidate (cells with |row - col| > k are "infinite"): D[m][m] <= k is decided
 // exactly.  A matching window is counted only by its canonical witness.
-__global__ void __launch_bounds__(128) filter_verify_kernel(const FilterArgs a) {
+__global__ void __launch_bounds__(128) filter_verify_kernel(const __grid_constant__ FilterArgs a) {
     if (*a.overflow) return;  // the band kernel takes this round instead
     const unsigned long long n = min(*a.ncand, a.cap);
     constexpr int INF = 1 << 20;
