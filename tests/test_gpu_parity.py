@@ -621,12 +621,20 @@ def test_one_shot_api_two_gpus_single_process():
     k = 3
     apm_b200.set_option("gpus", "1")
     want = apm_b200.count_matches(text, pats, k)
+    _, want_hits, want_n = apm_b200.find_matches(text, pats, k)
     apm_b200.set_option("gpus", "2")
     for reduce in ("auto", "nccl", "host"):  # NCCL all-reduce of the count vectors over NVLink / host-side sum
         apm_b200.set_option("reduce", reduce)
         for shard in ("db", "patterns", "auto"):
             apm_b200.set_option("shard", shard)
             assert apm_b200.count_matches(text, pats, k) == want, (reduce, shard)
+    apm_b200.set_option("reduce", "auto")
+    for mode in ("filter", "band"):  # the exact shortcut modes and the match positions shard the same way
+        apm_b200.set_option("mode", mode)
+        for shard in ("db", "patterns"):
+            apm_b200.set_option("shard", shard)
+            counts, hits, n_hits = apm_b200.find_matches(text, pats, k)
+            assert counts == want and hits == want_hits and n_hits == want_n, (mode, shard)
 
 
 def test_device_memory_cache_release_and_limits():
