@@ -92,6 +92,9 @@ int apm_find_matches(const unsigned char *text, size_t n_bytes, const char *cons
  *   "reduce"  = "auto" | "nccl" | "host"   how the per-GPU count vectors of the one-shot API are combined when
  *                 "gpus" > 1: one in-place ncclAllReduce per device (NCCL loaded at run time; auto falls back to
  *                 the host-side sum when libnccl.so.2 is not loadable)
+ *   "text_chunk_mb" = one-shot API: a GPU's shard with more than this many Mi window starts (default 32768) is
+ *                 streamed through two device buffers, segment by segment with its own halo, so the device memory
+ *                 needed is bounded for any text size; the copy of the next segment overlaps the counting
  *   "cache_mb" = device memory (MiB) kept cached between calls instead of cudaFree'd (default 4096)
  *   "rblock"  = "1" | "2" | "4" | "auto"     patterns register-blocked per thread (row-parallel kernel)
  *   "tile"    = window starts per CTA tile (multiple of 256) or "auto"   (row-parallel kernel)

@@ -70,6 +70,7 @@ struct Options {
     int cell = -1;   // DP-cell code of the sliced/band kernels: -1 auto, 0 = 5 LOP3, 1 = 4 LOP3 + 3 IMAD, 2 = 4 LOP3 + 2 IMAD
     int reduce = 0;  // multi-GPU count reduction: 0 auto (NCCL when loadable), 1 nccl, 2 host sum
     long long dp_scratch_mb = 256;
+    long long text_chunk_mb = 32768;  // one-shot API: a shard larger than this is streamed through two device buffers
     long long filter_cand_mb = 128;  // candidate buffer of the seed filter (mode=filter), MiB
     long long cache_mb = 4096;  // device memory kept for reuse between calls (dev_alloc / dev_free)
 };
@@ -990,6 +991,10 @@ int apm_set_option(const char *key, const char *value) {
         else if (v == "nccl") g_opt.reduce = 1;
         else if (v == "host") g_opt.reduce = 2;
         else return bad();
+    } else if (k == "text_chunk_mb") {
+        long long mb = atoll(value);
+        if (mb < 1 || mb > (1ll << 24)) return bad();
+        g_opt.text_chunk_mb = mb;
     } else if (k == "filter_cand_mb") {
         long long mb = atoll(value);
         if (mb < 1 || mb > 16384) return bad();
@@ -1022,6 +1027,7 @@ const char *apm_get_option(const char *key) {
     else if (k == "variant") tl_optbuf = std::to_string(o.variant);
     else if (k == "cell") tl_optbuf = o.cell == 2 ? "fma" : (o.cell == 1 ? "fma3" : (o.cell == 0 ? "lop3" : "auto"));
     else if (k == "reduce") tl_optbuf = o.reduce == 1 ? "nccl" : (o.reduce == 2 ? "host" : "auto");
+    else if (k == "text_chunk_mb") tl_optbuf = std::to_string(o.text_chunk_mb);
     else if (k == "filter_cand_mb") tl_optbuf = std::to_string(o.filter_cand_mb);
     else if (k == "cache_mb") tl_optbuf = std::to_string(o.cache_mb);
     else if (k == "dp_scratch_mb") tl_optbuf = std::to_string(o.dp_scratch_mb);
@@ -1329,7 +1335,8 @@ struct DevJob {
     int dev = 0;
     cudaStream_t st = nullptr, copy_st = nullptr;  // count kernels / H2D copies of the file ingest
     apm_plan *plan = nullptr;
-    uint8_t *d_text = nullptr;
+    uint8_t *d_text = nullptr, *d_text2 = nullptr;  // second buffer: segmented shards (text_chunk_mb)
+    cudaEvent_t seg_done[2] = {nullptr, nullptr};   // counting on buffer b has finished
     unsigned long long *d_hits = nullptr;  // [0] counter, [1..] packed hits (apm_find_matches)
     long long j0 = 0, j1 = 0, b0 = 0, b1 = 0;  // window-start range and byte range (global)
 };
@@ -1340,6 +1347,9 @@ void release_jobs(std::vector<DevJob> &jobs, int restore_dev) {
         if (j.st) cudaStreamSynchronize(j.st);
         if (j.plan) apm_plan_destroy(j.plan);
         if (j.d_text) dev_free(j.d_text);
+        if (j.d_text2) dev_free(j.d_text2);
+        for (auto &e : j.seg_done)
+            if (e) cudaEventDestroy(e);
         if (j.d_hits) dev_free(j.d_hits);
         if (j.st) cudaStreamDestroy(j.st);
         if (j.copy_st) cudaStreamDestroy(j.copy_st);
@@ -1363,8 +1373,16 @@ extern "C++" template <typename OnChunk>
 int copy_range_to_device(const TextSource &src, long long b0, long long b1, uint8_t *d_dst, cudaStream_t st,
                          cudaStream_t copy_st, OnChunk on_chunk) {
     if (b1 <= b0) return APM_OK;
-    if (src.host) {
-        CUDA_TRY(cudaMemcpyAsync(d_dst, src.host + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
+    if (src.host) {  // one async copy; on the copy stream when there is one (the count stream then waits for it)
+        CUDA_TRY(cudaMemcpyAsync(d_dst, src.host + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, copy_st ? copy_st : st));
+        if (copy_st) {
+            cudaEvent_t ev;
+            CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            cudaError_t e = cudaEventRecord(ev, copy_st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev, 0);
+            cudaEventDestroy(ev);
+            if (e != cudaSuccess) return fail(APM_ECUDA, "H2D copy: %s", cudaGetErrorString(e));
+        }
         return APM_OK;
     }
     const size_t chunk = kPinnedChunk;
@@ -1463,7 +1481,7 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
         j.dev = (restore + g) % ndev;  // the current device first
         if (cudaSetDevice(j.dev) != cudaSuccess) return bail(fail(APM_ECUDA, "cudaSetDevice(%d) failed", j.dev));
         if (cudaStreamCreateWithFlags(&j.st, cudaStreamNonBlocking) != cudaSuccess ||
-            (!src.host && cudaStreamCreateWithFlags(&j.copy_st, cudaStreamNonBlocking) != cudaSuccess))
+            cudaStreamCreateWithFlags(&j.copy_st, cudaStreamNonBlocking) != cudaSuccess)
             return bail(fail(APM_ECUDA, "cudaStreamCreate failed on device %d", g));
         mark("stream create", nullptr);
         if ((rc = apm_plan_create(patterns, pattern_len, nb_patterns, approx_factor, &j.plan))) return bail(rc);
@@ -1485,28 +1503,51 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
         }
         j.b0 = j.j0;
         j.b1 = std::min(N, j.j1 + mmax - 1);
-        if (dev_alloc((void **)&j.d_text, (size_t)std::max<long long>(16, j.b1 - j.b0)) != cudaSuccess)
-            return bail(fail(APM_ENOMEM, "cudaMalloc of %lld text bytes failed on device %d", j.b1 - j.b0, g));
+        // A shard of more than text_chunk_mb window starts is streamed through two device buffers, segment by
+        // segment (each with its own m_max - 1 halo): the copy of segment s+1 overlaps the counting of segment s and
+        // the device memory needed is bounded whatever the size of the text.
+        const long long seg_w = std::max<long long>(1, opt.text_chunk_mb) << 20;
+        const long long nseg = std::max<long long>(1, (j.j1 - j.j0 + seg_w - 1) / seg_w);
+        const long long seg_bytes = nseg == 1 ? j.b1 - j.b0 : seg_w + mmax - 1;
+        if (dev_alloc((void **)&j.d_text, (size_t)std::max<long long>(16, seg_bytes)) != cudaSuccess ||
+            (nseg > 1 && dev_alloc((void **)&j.d_text2, (size_t)std::max<long long>(16, seg_bytes)) != cudaSuccess))
+            return bail(fail(APM_ENOMEM, "cudaMalloc of %lld text bytes failed on device %d", seg_bytes, g));
         mark("text malloc", nullptr);
-        // file source: the windows whose bytes (incl. the m_max - 1 halo) have arrived are counted on j.st while
-        // the host is still reading the next chunk; only the tail of the shard waits for the last chunk
-        long long counted_to = j.j0;
-        auto on_chunk = [&](long long bytes_end, cudaEvent_t ev) -> int {
-            const long long w_end = bytes_end >= j.b1 ? j.j1 : std::min(j.j1, bytes_end - (mmax - 1));
-            if (w_end - counted_to < (bytes_end >= j.b1 ? 1 : (long long)(8 << 20))) return APM_OK;  // batch small steps
-            if (cudaStreamWaitEvent(j.st, ev, 0) != cudaSuccess) return fail(APM_ECUDA, "cudaStreamWaitEvent failed");
-            const int r = apm_plan_count_device(j.plan, j.d_text, (unsigned long long)j.b0, (unsigned long long)(j.b1 - j.b0),
-                                                (unsigned long long)N, (unsigned long long)counted_to,
-                                                (unsigned long long)w_end, j.st);
-            counted_to = w_end;
-            return r;
-        };
-        if ((rc = copy_range_to_device(src, j.b0, j.b1, j.d_text, j.st, j.copy_st, on_chunk))) return bail(rc);
-        mark("text H2D", src.host ? j.st : nullptr);
-        if (counted_to < j.j1 &&
-            (rc = apm_plan_count_device(j.plan, j.d_text, (unsigned long long)j.b0, (unsigned long long)(j.b1 - j.b0),
-                                        (unsigned long long)N, (unsigned long long)counted_to, (unsigned long long)j.j1, j.st)))
-            return bail(rc);
+        for (long long sgi = 0; sgi < nseg; ++sgi) {
+            const long long w0 = j.j0 + sgi * seg_w, w1 = std::min(j.j1, w0 + seg_w);
+            const long long sb0 = w0, sb1 = std::min(N, w1 + mmax - 1);
+            const int bi = (int)(sgi & 1);
+            uint8_t *d_seg = bi ? j.d_text2 : j.d_text;
+            if (nseg > 1) {
+                if (!j.seg_done[bi]) {
+                    if (cudaEventCreateWithFlags(&j.seg_done[bi], cudaEventDisableTiming) != cudaSuccess)
+                        return bail(fail(APM_ECUDA, "cudaEventCreate failed"));
+                } else if (cudaStreamWaitEvent(j.copy_st, j.seg_done[bi], 0) != cudaSuccess) {  // buffer still being counted
+                    return bail(fail(APM_ECUDA, "cudaStreamWaitEvent failed"));
+                }
+            }
+            // file source: the windows whose bytes (incl. the halo) have arrived are counted on j.st while the host
+            // is still reading the next 32 MiB chunk; only the tail of the segment waits for its last chunk
+            long long counted_to = w0;
+            auto on_chunk = [&](long long bytes_end, cudaEvent_t ev) -> int {
+                const long long w_end = bytes_end >= sb1 ? w1 : std::min(w1, bytes_end - (mmax - 1));
+                if (w_end - counted_to < (bytes_end >= sb1 ? 1 : (long long)(8 << 20))) return APM_OK;  // batch small steps
+                if (cudaStreamWaitEvent(j.st, ev, 0) != cudaSuccess) return fail(APM_ECUDA, "cudaStreamWaitEvent failed");
+                const int r = apm_plan_count_device(j.plan, d_seg, (unsigned long long)sb0, (unsigned long long)(sb1 - sb0),
+                                                    (unsigned long long)N, (unsigned long long)counted_to,
+                                                    (unsigned long long)w_end, j.st);
+                counted_to = w_end;
+                return r;
+            };
+            if ((rc = copy_range_to_device(src, sb0, sb1, d_seg, j.st, j.copy_st, on_chunk))) return bail(rc);
+            if (sgi == 0) mark("text H2D", src.host ? j.st : nullptr);
+            if (counted_to < w1 &&
+                (rc = apm_plan_count_device(j.plan, d_seg, (unsigned long long)sb0, (unsigned long long)(sb1 - sb0),
+                                            (unsigned long long)N, (unsigned long long)counted_to, (unsigned long long)w1, j.st)))
+                return bail(rc);
+            if (nseg > 1 && cudaEventRecord(j.seg_done[bi], j.st) != cudaSuccess)
+                return bail(fail(APM_ECUDA, "cudaEventRecord failed"));
+        }
         mark("count kernels", j.st);
     }
     // ---- combine the per-GPU count vectors

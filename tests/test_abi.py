@@ -53,7 +53,7 @@ def test_option_validation():
     apm_b200.set_option("shard", "DB_OVER_RANKS")
     assert apm_b200.get_option("shard") == "db"
     apm_b200.set_option("shard", "auto")
-    for key, val in (("kernel", "cpu"), ("cell", "bogus"), ("reduce", "mpi"), ("gpus", "0"), ("rblock", "3"), ("tile", "100"), ("nope", "1")):
+    for key, val in (("kernel", "cpu"), ("cell", "bogus"), ("reduce", "mpi"), ("text_chunk_mb", "0"), ("mode", "fast"), ("gpus", "0"), ("rblock", "3"), ("tile", "100"), ("nope", "1")):
         with pytest.raises(apm_b200.ApmError) as ei:
             apm_b200.set_option(key, val)
         assert ei.value.code == apm_b200.APM_EINVAL

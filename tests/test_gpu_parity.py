@@ -710,3 +710,26 @@ def test_find_matches_capacity_and_golden():
     assert hits == sorted(hits)
     counts, hits, n_hits = apm_b200.find_matches(FX[case["text"]], case["patterns"], case["k"], max_hits=0)
     assert counts == case["expected"] and hits == [] and n_hits == 0
+
+
+@pytest.mark.parametrize("mode", ["direct", "filter"])
+def test_one_shot_api_streams_large_shards_in_segments(tmp_path, mode):
+    """text_chunk_mb = 1: a 5.3 MB text goes through two 1 MiB (+halo) device buffers, six segments; patterns planted
+    across every segment seam, match positions, host-buffer and file entry points."""
+    n = 5_300_000
+    text = oracle.synth_text(0x5EED0001, 808, n).tobytes()
+    seg = 1 << 20
+    pats = [text[s * seg - 20:s * seg + 44] for s in range(1, 6)] + [text[seg - 1:seg + 199], text[-50:] + b"ACGTACGT"]
+    k = 2
+    apm_b200.set_option("mode", mode)
+    want, want_hits, want_n = apm_b200.find_matches(text, pats, k)
+    assert all(w >= 1 for w in want)
+    f = tmp_path / "t.fa"
+    f.write_bytes(text)
+    apm_b200.set_option("text_chunk_mb", "1")
+    try:
+        assert apm_b200.count_matches(text, pats, k) == want
+        assert apm_b200.find_matches(text, pats, k) == (want, want_hits, want_n)
+        assert apm_b200.count_matches_file(str(f), pats, k) == want
+    finally:
+        apm_b200.set_option("text_chunk_mb", "32768")
