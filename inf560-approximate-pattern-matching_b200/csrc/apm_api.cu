@@ -838,14 +838,17 @@ int launch_dp(apm_plan *pl, const uint8_t *d_buf, long long buf_offset, long lon
                 const long long threads = (long long)np * pl->tail_width;
                 const unsigned blocks = (unsigned)((threads + 127) / 128);
                 const long long stride = (long long)blocks * 128;
-                int rc = ensure_scratch(pl, (size_t)stride * per_thread);
+                const bool banded = pl->opt.mode != MODE_DIRECT && pl->k <= kBandDpMaxK;
+                int rc = banded ? APM_OK : ensure_scratch(pl, (size_t)stride * per_thread);
                 if (rc) return rc;
                 a.pat_list = pl->d_tail_list + p0;
                 a.npat = np;
                 a.tail_width = pl->tail_width;
                 a.scratch = pl->d_scratch;
                 a.scratch_stride = stride;
-                dp_tail_kernel<<<blocks, 128, 0, st>>>(a);
+                // direct mode: every cell of the (truncated) window; band / filter mode: only the band that decides
+                if (banded) dp_tail_band_kernel<<<blocks, 128, 0, st>>>(a);
+                else dp_tail_kernel<<<blocks, 128, 0, st>>>(a);
                 CUDA_TRY(cudaGetLastError());
                 g_launches++;
             }

@@ -57,6 +57,37 @@ __device__ __forceinline__ uint32_t dp_window(const uint8_t *__restrict__ pat, c
     return last;
 }
 
+// Banded version of the same DP for the DECISION distance <= k (k <= kBandDpMaxK): cells with |row - col| > k are
+// treated as infinite, which leaves every value <= k exact (Ukkonen).  One row of 2k+1 cells in local memory, no
+// global scratch, early exit when a whole row exceeds k.  Used by the filter's verification and, in the exact
+// shortcut modes, for the truncated tail windows (size x size instead of m x m).
+constexpr int kBandDpMaxK = 16;
+__device__ __forceinline__ bool band_dp_within_k(const uint8_t *__restrict__ P, const uint8_t *__restrict__ W, int size, int k) {
+    constexpr int INF = 1 << 20;
+    int band[2 * kBandDpMaxK + 3];  // band[x] = D[r][r + x - k]
+    for (int x = 0; x <= 2 * k; ++x) band[x] = x >= k ? x - k : INF;  // row 0: D[0][c] = c
+    band[2 * k + 1] = INF;
+    for (int r = 1; r <= size; ++r) {
+        const uint32_t pc = P[r - 1];
+        int left = INF, best = INF;
+        for (int x = 0; x <= 2 * k; ++x) {
+            const int col = r + x - k;
+            int v;
+            if (col < 0 || col > size) v = INF;
+            else if (col == 0) v = r;
+            else {
+                const int diag = band[x] + (pc == W[col - 1] ? 0 : 1);
+                v = min(diag, min(band[x + 1], left) + 1);
+            }
+            band[x] = v;  // band[x + 1] (row r-1) is still untouched when the next x reads it as "diag"
+            left = v;
+            best = min(best, v);
+        }
+        if (best > k) return false;
+    }
+    return band[k] <= k;
+}
+
 // Tail mode: thread (p, t) evaluates window j = max(0, n_total - m_p + 1) + t if it lies in
 // [j_begin, j_end).  All such windows are truncated (size < m) -- or the whole text is shorter
 // than the pattern.
@@ -76,6 +107,26 @@ __global__ void __launch_bounds__(128) dp_tail_kernel(const DpArgs a) {
     const uint32_t d = dp_window(a.pat_bytes + a.pat_off[p], a.buf + (j - a.buf_offset), size,
                                  a.scratch + gtid, a.scratch_stride);
     if (d <= (uint32_t)a.k) {
+        atomicAdd(&a.counts[p], 1ull);
+        if (a.sink.buf) hit_emit(a.sink, p, j);
+    }
+}
+
+// Tail mode with the banded DP (exact shortcut modes, k <= kBandDpMaxK): same mapping, no scratch.
+__global__ void __launch_bounds__(128) dp_tail_band_kernel(const DpArgs a) {
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)a.npat * a.tail_width;
+    if (gtid >= total) return;
+    const int pi = (int)(gtid / a.tail_width);
+    const int t = (int)(gtid % a.tail_width);
+    const int p = a.pat_list[pi];
+    const int m = a.pat_len[p];
+    const long long first = a.n_total - m + 1 > 0 ? a.n_total - m + 1 : 0;
+    const long long j = first + t;
+    if (j < a.j_begin || j >= a.j_end) return;
+    const long long left = a.n_total - j;
+    const int size = left < m ? (int)left : m;
+    if (size <= a.k || band_dp_within_k(a.pat_bytes + a.pat_off[p], a.buf + (j - a.buf_offset), size, a.k)) {
         atomicAdd(&a.counts[p], 1ull);
         if (a.sink.buf) hit_emit(a.sink, p, j);
     }

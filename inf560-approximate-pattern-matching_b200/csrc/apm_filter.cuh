@@ -19,12 +19,13 @@
 // Work: O(text bytes) + O(candidates * m * (2k+1)) instead of O(text bytes * patterns * m * (2k+1)).
 #pragma once
 #include "apm_common.cuh"
+#include "apm_dp.cuh"
 
 namespace apm {
 
 constexpr int kFilterMinSeed = 8;
 constexpr int kFilterMaxSeed = 16;
-constexpr int kFilterMaxK = 16;
+constexpr int kFilterMaxK = 16;  // == kBandDpMaxK (apm_dp.cuh)
 constexpr int kFilterThreads = 512;
 constexpr int kFilterPosPerThread = 16;
 constexpr uint32_t kFilterHashB = 0x9E3779B1u;
@@ -261,7 +262,6 @@ __global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const __gri
 __global__ void __launch_bounds__(128) filter_verify_kernel(const __grid_constant__ FilterArgs a) {
     if (*a.overflow) return;  // the band kernel takes this round instead
     const unsigned long long n = min(*a.ncand, a.cap);
-    constexpr int INF = 1 << 20;
     const int k = a.k;
     for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < n;
          c += (unsigned long long)gridDim.x * blockDim.x) {
@@ -272,29 +272,7 @@ __global__ void __launch_bounds__(128) filter_verify_kernel(const __grid_constan
         const int m = __ldg(a.fp_m + slot);
         const uint8_t *P = a.pat_bytes + __ldg(a.fp_off + slot);
         const uint8_t *W = a.buf + j;
-        int band[2 * kFilterMaxK + 3];  // band[x] = D[r][r + x - k]
-        for (int x = 0; x <= 2 * k; ++x) band[x] = x >= k ? x - k : INF;  // row 0: D[0][c] = c
-        band[2 * k + 1] = INF;
-        bool alive = true;
-        for (int r = 1; r <= m && alive; ++r) {
-            const uint32_t pc = P[r - 1];
-            int left = INF, best = INF;
-            for (int x = 0; x <= 2 * k; ++x) {
-                const int col = r + x - k;
-                int v;
-                if (col < 0 || col > m) v = INF;
-                else if (col == 0) v = r;
-                else {
-                    const int diag = band[x] + (pc == W[col - 1] ? 0 : 1);
-                    v = min(diag, min(band[x + 1], left) + 1);
-                }
-                band[x] = v;  // band[x + 1] (row r-1) is still untouched when the next x reads it as "diag"
-                left = v;
-                best = min(best, v);
-            }
-            alive = best <= k;
-        }
-        if (!alive || band[k] > k) continue;
+        if (!band_dp_within_k(P, W, m, k)) continue;
         // canonical witness: no (piece', shift') < (piece, shift) whose seed occurs inside the window
         bool canonical = true;
         for (int i2 = 0; i2 <= piece && canonical; ++i2) {
