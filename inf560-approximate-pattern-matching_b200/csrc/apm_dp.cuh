@@ -62,16 +62,23 @@ __device__ __forceinline__ uint32_t dp_window(const uint8_t *__restrict__ pat, c
 // global scratch, early exit when a whole row exceeds k.  Used by the filter's verification and, in the exact
 // shortcut modes, for the truncated tail windows (size x size instead of m x m).
 constexpr int kBandDpMaxK = 16;
-__device__ __forceinline__ bool band_dp_within_k(const uint8_t *__restrict__ P, const uint8_t *__restrict__ W, int size, int k) {
+
+// KB = compile-time band half-width >= k (a wider band is just as exact): the row lives in registers and the
+// sweep over its 2 KB + 1 cells is fully unrolled, so a row costs one dependent min/add chain instead of a chain
+// of local-memory round trips.
+template <int KB>
+__device__ __forceinline__ bool band_dp_within_k_t(const uint8_t *__restrict__ P, const uint8_t *__restrict__ W, int size, int k) {
     constexpr int INF = 1 << 20;
-    int band[2 * kBandDpMaxK + 3];  // band[x] = D[r][r + x - k]
-    for (int x = 0; x <= 2 * k; ++x) band[x] = x >= k ? x - k : INF;  // row 0: D[0][c] = c
-    band[2 * k + 1] = INF;
+    int band[2 * KB + 2];  // band[x] = D[r][r + x - KB]
+#pragma unroll
+    for (int x = 0; x <= 2 * KB; ++x) band[x] = x >= KB ? x - KB : INF;  // row 0: D[0][c] = c
+    band[2 * KB + 1] = INF;
     for (int r = 1; r <= size; ++r) {
         const uint32_t pc = P[r - 1];
         int left = INF, best = INF;
-        for (int x = 0; x <= 2 * k; ++x) {
-            const int col = r + x - k;
+#pragma unroll
+        for (int x = 0; x <= 2 * KB; ++x) {
+            const int col = r + x - KB;
             int v;
             if (col < 0 || col > size) v = INF;
             else if (col == 0) v = r;
@@ -85,7 +92,16 @@ __device__ __forceinline__ bool band_dp_within_k(const uint8_t *__restrict__ P, 
         }
         if (best > k) return false;
     }
-    return band[k] <= k;
+    return band[KB] <= k;
+}
+
+__device__ __forceinline__ bool band_dp_within_k(const uint8_t *__restrict__ P, const uint8_t *__restrict__ W, int size, int k) {
+    if (k <= 2) return band_dp_within_k_t<2>(P, W, size, k);
+    if (k <= 4) return band_dp_within_k_t<4>(P, W, size, k);
+    if (k <= 6) return band_dp_within_k_t<6>(P, W, size, k);
+    if (k <= 8) return band_dp_within_k_t<8>(P, W, size, k);
+    if (k <= 12) return band_dp_within_k_t<12>(P, W, size, k);
+    return band_dp_within_k_t<16>(P, W, size, k);
 }
 
 // Tail mode: thread (p, t) evaluates window j = max(0, n_total - m_p + 1) + t if it lies in
