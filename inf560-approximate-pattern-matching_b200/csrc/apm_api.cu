@@ -245,7 +245,9 @@ struct FilterSet {
     long long *d_fp_off = nullptr;
     uint64_t *d_cand = nullptr;
     unsigned long long cap = 0;
-    unsigned long long *d_ctr = nullptr;  // [0] candidates, [1] (low word) overflow flag
+    uint64_t *d_long = nullptr;           // long-lived candidates (finished by whole warps)
+    unsigned long long long_cap = 0;
+    unsigned long long *d_ctr = nullptr;  // [0] candidates, [1] (low word) overflow flag, [2] long-lived candidates
 };
 
 template <typename T>
@@ -320,6 +322,7 @@ void free_work(apm_plan *pl) {
     dev_free(f.d_fp_off);
     dev_free(f.d_cand);
     dev_free(f.d_ctr);
+    dev_free(f.d_long);
     f = FilterSet();
     dev_free(pl->d_tail_list);
     dev_free(pl->d_all_list);
@@ -479,7 +482,9 @@ int build_filter(apm_plan *pl) {
     if ((rc = upload(&f.d_fp_off, fp_off))) return rc;
     f.cap = (unsigned long long)std::max<long long>(1, pl->opt.filter_cand_mb) * ((1ull << 20) / sizeof(uint64_t));
     CUDA_TRY(dev_alloc((void **)&f.d_cand, f.cap * sizeof(uint64_t)));
-    CUDA_TRY(dev_alloc((void **)&f.d_ctr, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(dev_alloc((void **)&f.d_ctr, 3 * sizeof(unsigned long long)));
+    f.long_cap = std::max<unsigned long long>(1024, f.cap / 8);
+    CUDA_TRY(dev_alloc((void **)&f.d_long, f.long_cap * sizeof(uint64_t)));
     return APM_OK;
 }
 
@@ -773,13 +778,16 @@ int launch_filter(apm_plan *pl, const uint8_t *d_buf, long long buf_len, long lo
     a.cap = f.cap;
     a.ncand = f.d_ctr;
     a.overflow = reinterpret_cast<unsigned int *>(f.d_ctr + 1);
+    a.nlong = f.d_ctr + 2;
+    a.longq = f.d_long;
+    a.longcap = f.long_cap;
     a.counts = pl->d_counts;
     a.sink = pl->sink;
     const long long round = 1ll << kFilterSlabLog;
     for (long long r0 = w0; r0 < lim; r0 += round) {
         a.w0 = r0;
         a.w1 = std::min(lim, r0 + round);
-        CUDA_TRY(cudaMemsetAsync(f.d_ctr, 0, 2 * sizeof(unsigned long long), st));
+        CUDA_TRY(cudaMemsetAsync(f.d_ctr, 0, 3 * sizeof(unsigned long long), st));
         const long long positions = a.w1 - a.w0 + f.mmax;
         const long long tiles = (positions + kFilterThreads * kFilterPosPerThread - 1) / (kFilterThreads * kFilterPosPerThread);
         // persistent CTAs (3 per SM: 64 KB digest each), every CTA strides over the tiles
@@ -799,7 +807,9 @@ int launch_filter(apm_plan *pl, const uint8_t *d_buf, long long buf_len, long lo
         CUDA_TRY(le);
         filter_verify_kernel<<<pl->num_sms * 16, 128, 0, st>>>(a);
         CUDA_TRY(cudaGetLastError());
-        g_launches += 2;
+        filter_verify_long_kernel<<<pl->num_sms * 8, 128, 0, st>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 3;
         int rc;
         for (auto &b : pl->fb_buckets)
             if ((rc = launch_myers(pl, b, d_buf, buf_len, n_end, a.w0, a.w1, st, a.overflow))) return rc;

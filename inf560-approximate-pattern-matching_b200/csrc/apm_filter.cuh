@@ -71,6 +71,9 @@ struct FilterArgs {
     unsigned long long cap;
     unsigned long long *ncand;    // zeroed before the scan
     unsigned int *overflow;       // zeroed before the scan; set when cand is full
+    uint64_t *longq;              // candidates still alive after kFilterShortRows rows: finished by whole warps
+    unsigned long long longcap;
+    unsigned long long *nlong;    // zeroed before the scan
     unsigned long long *counts;
     HitSink sink;                 // optional match-position output
 };
@@ -257,8 +260,27 @@ __global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const __gri
     filter_flush(a, stg);
 }
 
-// Verify: banded DP of one candidate (cells with |row - col| > k are "infinite"): D[m][m] <= k is decided
-// exactly.  A matching window is counted only by its canonical witness.
+// canonical witness: no (piece', shift') < (piece, shift) whose seed occurs inside the window
+__device__ __forceinline__ bool filter_is_canonical(const uint8_t *P, const uint8_t *W, int m, int k, int s, int piece, int dk) {
+    for (int i2 = 0; i2 <= piece; ++i2) {
+        const int o2 = filter_piece_offset(i2, m, k);
+        const int dmax = i2 == piece ? dk - 1 : 2 * k;
+        for (int d2 = 0; d2 <= dmax; ++d2) {
+            const int off = o2 + d2 - k;
+            if (off < 0 || off + s > m) continue;
+            bool same = true;
+            for (int x = 0; x < s && same; ++x) same = P[o2 + x] == W[off + x];
+            if (same) return false;
+        }
+    }
+    return true;
+}
+
+// Verify: banded DP of one candidate per thread (cells with |row - col| > k are "infinite"): D[m][m] <= k is
+// decided exactly.  A matching window is counted only by its canonical witness.  Random seed hits die within a
+// few rows; a candidate that is still alive after kFilterShortRows rows is almost certainly a real match and is
+// handed to filter_verify_long_kernel, where a whole warp finishes it.
+constexpr int kFilterShortRows = 32;
 __global__ void __launch_bounds__(128) filter_verify_kernel(const __grid_constant__ FilterArgs a) {
     if (*a.overflow) return;  // the band kernel takes this round instead
     const unsigned long long n = min(*a.ncand, a.cap);
@@ -272,21 +294,51 @@ __global__ void __launch_bounds__(128) filter_verify_kernel(const __grid_constan
         const int m = __ldg(a.fp_m + slot);
         const uint8_t *P = a.pat_bytes + __ldg(a.fp_off + slot);
         const uint8_t *W = a.buf + j;
-        if (!band_dp_within_k(P, W, m, k)) continue;
-        // canonical witness: no (piece', shift') < (piece, shift) whose seed occurs inside the window
-        bool canonical = true;
-        for (int i2 = 0; i2 <= piece && canonical; ++i2) {
-            const int o2 = filter_piece_offset(i2, m, k);
-            const int dmax = i2 == piece ? dk - 1 : 2 * k;
-            for (int d2 = 0; d2 <= dmax && canonical; ++d2) {
-                const int off = o2 + d2 - k;
-                if (off < 0 || off + a.s > m) continue;
-                bool same = true;
-                for (int x = 0; x < a.s && same; ++x) same = P[o2 + x] == W[off + x];
-                if (same) canonical = false;
+        int st = band_dp_status(P, W, m, k, kFilterShortRows);
+        if (st == 2) {
+            if (k <= 15) {
+                const unsigned long long pos = atomicAdd(a.nlong, 1ull);
+                if (pos < a.longcap) {
+                    a.longq[pos] = e;
+                    continue;
+                }
             }
+            st = band_dp_status(P, W, m, k, 0x7FFFFFFF);  // queue full (or k = 16): finish here
         }
-        if (canonical) {
+        if (st != 1 || !filter_is_canonical(P, W, m, k, a.s, piece, dk)) continue;
+        atomicAdd(&a.counts[__ldg(a.fp_id + slot)], 1ull);
+        if (a.sink.buf) hit_emit(a.sink, __ldg(a.fp_id + slot), j);
+    }
+}
+
+// One warp per long-lived candidate: warp-parallel banded DP, then the canonical-witness test spread over the lanes.
+__global__ void __launch_bounds__(128) filter_verify_long_kernel(const __grid_constant__ FilterArgs a) {
+    if (*a.overflow) return;
+    const unsigned long long n = min(*a.nlong, a.longcap);
+    const int k = a.k, lane = threadIdx.x & 31;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long c = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < n; c += nwarps) {
+        const uint64_t e = a.longq[c];
+        const uint32_t slot = (uint32_t)(e >> 40);
+        const int piece = (int)((e >> 34) & 63), dk = (int)((e >> 28) & 63);
+        const long long j = a.w0 + (long long)(e & 0xFFFFFFFu);
+        const int m = __ldg(a.fp_m + slot);
+        const uint8_t *P = a.pat_bytes + __ldg(a.fp_off + slot);
+        const uint8_t *W = a.buf + j;
+        if (!band_dp_within_k_warp(P, W, m, k)) continue;  // warp-uniform
+        // smaller witnesses (piece', shift') in linear order q = piece' * (2k+1) + shift'; lane l tests q = l, l+32, ..
+        const int nq = piece * (2 * k + 1) + dk;
+        bool found = false;
+        for (int q = lane; q < nq && !found; q += 32) {
+            const int i2 = q / (2 * k + 1), d2 = q - i2 * (2 * k + 1);
+            const int o2 = filter_piece_offset(i2, m, k), off = o2 + d2 - k;
+            if (off < 0 || off + a.s > m) continue;
+            bool same = true;
+            for (int x = 0; x < a.s && same; ++x) same = P[o2 + x] == W[off + x];
+            found = same;
+        }
+        if (__any_sync(0xFFFFFFFFu, found)) continue;
+        if (lane == 0) {
             atomicAdd(&a.counts[__ldg(a.fp_id + slot)], 1ull);
             if (a.sink.buf) hit_emit(a.sink, __ldg(a.fp_id + slot), j);
         }
