@@ -29,7 +29,7 @@ constexpr int kFilterMaxK = 16;  // == kBandDpMaxK (apm_dp.cuh)
 constexpr int kFilterThreads = 512;
 constexpr int kFilterPosPerThread = 16;
 constexpr uint32_t kFilterHashB = 0x9E3779B1u;
-constexpr int kFilterSlabLog = 27;  // window starts per scan/verify round: candidates carry a 28-bit local start
+constexpr int kFilterSlabLog = 28;  // window starts per scan/verify round: candidates carry a 28-bit local start
 
 // table index of a seed hash (hb bits)
 // (the leading bits of the polynomial hash depend on every byte of the seed; no extra mixing step)

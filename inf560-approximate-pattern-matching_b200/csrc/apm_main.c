@@ -8,8 +8,11 @@
  * Extra knobs come from the environment so argv stays drop-in: APM_GPUS, APM_SHARD, APM_KERNEL, APM_MODE
  * (direct | band | filter -- all exact, same counts; the CLI defaults to filter), APM_CELL, APM_RBLOCK, APM_TILE; APM_INFO=1 adds the
  * "(Rank 0) - TOTAL TIME ..." line of the parallel binary (patterns_over_ranks.c:223-226); APM_POSITIONS=n
- * additionally lists the first n matches as "Match of pattern <p> at byte j" (not in the reference).
+ * additionally lists the first n matches as "Match of pattern <p> at byte j" (not in the reference);
+ * APM_PATTERN_FILE=path appends one pattern per line of that file to the patterns of argv (argv is limited to
+ * ~2 MB; with it `apm k file` without any argv pattern is accepted).
  */
+#define _GNU_SOURCE
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -26,7 +29,52 @@ static int set_from_env(const char *env, const char *key) {
     return 0;
 }
 
+/* patterns of APM_PATTERN_FILE appended to argv (one per line, empty lines skipped) */
+static char **with_pattern_file(int *argc, char **argv) {
+    const char *path = getenv("APM_PATTERN_FILE");
+    if (!path || !*path) return argv;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) {
+        fprintf(stderr, "Unable to open the pattern file <%s>\n", path);
+        exit(1);
+    }
+    int cap = *argc + 1024, n = *argc;
+    char **out = (char **)malloc(sizeof(char *) * (size_t)(cap + 2));
+    memcpy(out, argv, sizeof(char *) * (size_t)n);
+    char *line = NULL;
+    size_t lcap = 0;
+    ssize_t len;
+    while ((len = getline(&line, &lcap, fp)) >= 0) {
+        while (len > 0 && (line[len - 1] == '\n' || line[len - 1] == '\r')) line[--len] = 0;
+        if (len == 0) continue;
+        if (n == cap) {
+            cap *= 2;
+            out = (char **)realloc(out, sizeof(char *) * (size_t)(cap + 2));
+        }
+        out[n++] = strdup(line);
+    }
+    free(line);
+    fclose(fp);
+    out[n] = NULL;
+    *argc = n;
+    return out;
+}
+
 int main(int argc, char **argv) {
+    if (argc >= 3) { /* an explicit approach stays the LAST argv word: take it off before appending file patterns */
+        const char *lastw = argv[argc - 1];
+        const int has_flag = argc >= 4 && (!strcmp(lastw, "DB_OVER_RANKS") || !strcmp(lastw, "PATTERNS_OVER_RANKS"));
+        if (getenv("APM_PATTERN_FILE") && *getenv("APM_PATTERN_FILE")) {
+            int n = argc - (has_flag ? 1 : 0);
+            char **v = with_pattern_file(&n, argv);
+            if (has_flag) { /* with_pattern_file leaves room for it */
+                v[n++] = (char *)lastw;
+                v[n] = NULL;
+            }
+            argc = n;
+            argv = v;
+        }
+    }
     if (argc < 4) { /* sequential.c:35-41 */
         printf("Usage: %s approximation_factor dna_database pattern1 pattern2 ...\n", argv[0]);
         return 1;

@@ -733,3 +733,24 @@ def test_one_shot_api_streams_large_shards_in_segments(tmp_path, mode):
         assert apm_b200.count_matches_file(str(f), pats, k) == want
     finally:
         apm_b200.set_option("text_chunk_mb", "32768")
+
+
+def test_cli_pattern_file_positions_and_info(tmp_path):
+    """CLI extras that stay out of argv: APM_PATTERN_FILE (one pattern per line), APM_POSITIONS, APM_INFO, APM_MODE."""
+    case = next(c for c in CASES if c["name"] == "x100_k2")
+    f = tmp_path / "t.fa"
+    f.write_bytes(FX[case["text"]])
+    pf = tmp_path / "patterns.txt"
+    pf.write_bytes(b"\n".join(case["patterns"][1:]) + b"\n\n")
+    argv = [apm_b200.CLI_PATH, str(case["k"]), str(f), case["patterns"][0].decode(), "DB_OVER_RANKS"]
+    for mode in ("filter", "direct"):
+        env = dict(os.environ, APM_PATTERN_FILE=str(pf), APM_POSITIONS="5", APM_INFO="1", APM_MODE=mode, OMP_NUM_THREADS="3")
+        r = subprocess.run(argv, capture_output=True, text=True, env=env, check=True)
+        lines = r.stdout.splitlines()
+        counts = [int(l.rsplit(": ", 1)[1]) for l in lines if l.startswith("Number of matches for pattern <")]
+        assert counts == case["expected"], mode
+        assert any(l.startswith("(Rank 0) - TOTAL TIME using 1 mpi_ranks and 3 omp_thread(s) per rank:") for l in lines)
+        assert sum(l.startswith("Match of pattern <") for l in lines) == 5
+    r = subprocess.run([apm_b200.CLI_PATH, "1", str(f)], capture_output=True, text=True,
+                       env=dict(os.environ, APM_PATTERN_FILE=str(pf)), check=True)
+    assert sum(l.startswith("Number of matches") for l in r.stdout.splitlines()) == len(case["patterns"]) - 1
