@@ -89,9 +89,10 @@ int apm_find_matches(const unsigned char *text, size_t n_bytes, const char *cons
  *   "cell"    = "auto" | "lop3" | "fma3" | "fma"   code of one DP cell in the window-sliced / band kernels:
  *                 lop3: 5 LOP3 (ALU pipe only); fma3: 4 LOP3 + 3 IMAD; fma: 4 LOP3 + 2 IMAD (FMA pipe takes the
  *                 subtractions); auto (default) picks per pattern-length class.  Same results, different speed.
- *   "reduce"  = "auto" | "nccl" | "host"   how the per-GPU count vectors of the one-shot API are combined when
- *                 "gpus" > 1: one in-place ncclAllReduce per device (NCCL loaded at run time; auto falls back to
- *                 the host-side sum when libnccl.so.2 is not loadable)
+ *   "reduce"  = "auto" | "p2p" | "nccl" | "host"   how the per-GPU count vectors of the one-shot API are combined
+ *                 when "gpus" > 1: p2p = every GPU adds its vector into GPU 0's with system-scope atomics on NVLink
+ *                 peer memory (our own kernel, no communicator); nccl = one in-place ncclAllReduce per device (NCCL
+ *                 loaded at run time); host = host-side sum; auto (default) = p2p, else nccl, else host
  *   "text_chunk_mb" = one-shot API: a GPU's shard with more than this many Mi window starts (default 32768) is
  *                 streamed through two device buffers, segment by segment with its own halo, so the device memory
  *                 needed is bounded for any text size; the copy of the next segment overlaps the counting

@@ -68,7 +68,7 @@ struct Options {
     int tile = 0;    // 0 = auto
     int variant = 0; // column-step code variant (see myers_step_fma)
     int cell = -1;   // DP-cell code of the sliced/band kernels: -1 auto, 0 = 5 LOP3, 1 = 4 LOP3 + 3 IMAD, 2 = 4 LOP3 + 2 IMAD
-    int reduce = 0;  // multi-GPU count reduction: 0 auto (NCCL when loadable), 1 nccl, 2 host sum
+    int reduce = 0;  // multi-GPU count reduction: 0 auto (p2p kernel, else NCCL, else host), 1 nccl, 2 host sum, 3 p2p
     long long dp_scratch_mb = 256;
     long long text_chunk_mb = 32768;  // one-shot API: a shard larger than this is streamed through two device buffers
     long long filter_cand_mb = 128;  // candidate buffer of the seed filter (mode=filter), MiB
@@ -1003,6 +1003,7 @@ int apm_set_option(const char *key, const char *value) {
         if (v == "auto") g_opt.reduce = 0;
         else if (v == "nccl") g_opt.reduce = 1;
         else if (v == "host") g_opt.reduce = 2;
+        else if (v == "p2p") g_opt.reduce = 3;
         else return bad();
     } else if (k == "text_chunk_mb") {
         long long mb = atoll(value);
@@ -1039,7 +1040,7 @@ const char *apm_get_option(const char *key) {
     else if (k == "tile") tl_optbuf = o.tile ? std::to_string(o.tile) : "auto";
     else if (k == "variant") tl_optbuf = std::to_string(o.variant);
     else if (k == "cell") tl_optbuf = o.cell == 2 ? "fma" : (o.cell == 1 ? "fma3" : (o.cell == 0 ? "lop3" : "auto"));
-    else if (k == "reduce") tl_optbuf = o.reduce == 1 ? "nccl" : (o.reduce == 2 ? "host" : "auto");
+    else if (k == "reduce") tl_optbuf = o.reduce == 1 ? "nccl" : (o.reduce == 2 ? "host" : (o.reduce == 3 ? "p2p" : "auto"));
     else if (k == "text_chunk_mb") tl_optbuf = std::to_string(o.text_chunk_mb);
     else if (k == "filter_cand_mb") tl_optbuf = std::to_string(o.filter_cand_mb);
     else if (k == "cache_mb") tl_optbuf = std::to_string(o.cache_mb);
@@ -1565,7 +1566,42 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
     }
     // ---- combine the per-GPU count vectors
     bool reduced_on_device = false;
-    if (G > 1 && opt.reduce != 2) {
+    if (G > 1 && (opt.reduce == 0 || opt.reduce == 3)) {
+        // our own kernel over NVLink peer memory: GPU g adds its vector into GPU 0's with system-scope atomics
+        bool peers = true;
+        for (int g = 1; g < G && peers; ++g) {
+            int can = 0;
+            peers = cudaDeviceCanAccessPeer(&can, jobs[g].dev, jobs[0].dev) == cudaSuccess && can;
+        }
+        if (peers) {
+            for (int g = 1; g < G; ++g) {
+                cudaSetDevice(jobs[g].dev);
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(jobs[0].dev, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+                    return bail(fail(APM_ECUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", jobs[g].dev, jobs[0].dev, cudaGetErrorString(pe)));
+                cudaGetLastError();
+                peer_accumulate_kernel<<<(nb_patterns + 255) / 256, 256, 0, jobs[g].st>>>(jobs[g].plan->d_counts,
+                                                                                        jobs[0].plan->d_counts, nb_patterns);
+                g_launches++;
+                cudaEvent_t ev;
+                cudaError_t e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                if (e == cudaSuccess) {
+                    e = cudaEventRecord(ev, jobs[g].st);
+                    if (e == cudaSuccess) {
+                        cudaSetDevice(jobs[0].dev);
+                        e = cudaStreamWaitEvent(jobs[0].st, ev, 0);  // GPU 0 reads its vector after every contribution
+                    }
+                    cudaEventDestroy(ev);
+                }
+                if (e != cudaSuccess) return bail(fail(APM_ECUDA, "peer reduction: %s", cudaGetErrorString(e)));
+            }
+            reduced_on_device = true;
+        } else if (opt.reduce == 3) {
+            return bail(fail(APM_ECUDA, "reduce=p2p requested but the GPUs cannot access each other's memory"));
+        }
+    }
+    if (G > 1 && !reduced_on_device && opt.reduce != 2 && opt.reduce != 3) {
         std::lock_guard<std::mutex> lk(g_nccl_mu);
         if (nccl_load()) {
             std::vector<int> devs;

@@ -102,6 +102,18 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters,
     if (x == 0x12345678u) out[0] = x;  // practically never true; keeps the chains alive
 }
 
+// Sum of a GPU's count vector into another GPU's vector over NVLink peer memory: system-scope atomics on the
+// mapped peer pointer, one launch per contributing GPU on its own count stream.  Replaces the MPI_Send/MPI_Recv of
+// per-pattern ints of the reference (patterns_over_ranks.c:195,389; database_over_ranks.c:179,573) in the
+// single-process multi-GPU path: no communicator, no staging buffer, the transfer is the kernel's own stores.
+__global__ void __launch_bounds__(256) peer_accumulate_kernel(const unsigned long long *__restrict__ local,
+                                                              unsigned long long *peer, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long v = local[i];
+    if (v) atomicAdd_system(peer + i, v);
+}
+
 // integer instructions per thread per loop iteration of int_peak_kernel<KIND>
 __host__ inline double int_peak_ops_per_iter(int kind) {
     const double n = 8.0 * 8.0;  // rep x ILP

@@ -623,7 +623,7 @@ def test_one_shot_api_two_gpus_single_process():
     want = apm_b200.count_matches(text, pats, k)
     _, want_hits, want_n = apm_b200.find_matches(text, pats, k)
     apm_b200.set_option("gpus", "2")
-    for reduce in ("auto", "nccl", "host"):  # NCCL all-reduce of the count vectors over NVLink / host-side sum
+    for reduce in ("auto", "p2p", "nccl", "host"):  # peer-memory kernel / NCCL all-reduce over NVLink / host-side sum
         apm_b200.set_option("reduce", reduce)
         for shard in ("db", "patterns", "auto"):
             apm_b200.set_option("shard", shard)
