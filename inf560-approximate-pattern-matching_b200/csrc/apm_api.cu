@@ -430,7 +430,7 @@ int build_filter(apm_plan *pl) {
     f.hb = std::max(kFilterSmemLog + 1, std::min(27, lg + 12));  // <= 1/4096 of the bitmap set  // <= 1/512 of the bitmap set: the scan rarely leaves its fast path
     f.bs = 1u;
     for (int i = 0; i < f.s; ++i) f.bs *= kFilterHashB;
-    std::vector<uint32_t> bitmap((size_t)1 << (f.hb - 5), 0u), digest((size_t)1 << (kFilterSmemLog - 5), 0u);
+    std::vector<uint32_t> digest((size_t)1 << (kFilterSmemLog - 5), 0u);
     struct Ent { uint32_t idx, hash, slot; uint8_t piece; };
     std::vector<Ent> ents;
     ents.reserve((size_t)f.nent);
@@ -453,7 +453,6 @@ int build_filter(apm_plan *pl) {
             const int o = filter_piece_offset(i, m, k);
             const uint32_t hash = filter_hash((const uint8_t *)pat.data() + o, f.s);
             const uint32_t idx = filter_index(hash, f.hb);
-            bitmap[idx >> 5] |= 1u << (idx & 31);
             digest[filter_digest_word(hash)] |= filter_digest_mask(hash);
             ents.push_back({idx, hash, (uint32_t)slot, (uint8_t)i});
         }
@@ -470,11 +469,18 @@ int build_filter(apm_plan *pl) {
         e_piece.push_back(e.piece);
     }
     int rc;
-    if ((rc = upload(&f.d_bitmap, bitmap))) return rc;
+    // the full bitmap (2^hb bits, up to 16 MiB) is zeroed and filled on the device
+    const size_t bitmap_bytes = (size_t)1 << (f.hb - 3);
+    CUDA_TRY(dev_alloc((void **)&f.d_bitmap, bitmap_bytes));
+    CUDA_TRY(cudaMemsetAsync(f.d_bitmap, 0, bitmap_bytes, 0));
     if ((rc = upload(&f.d_digest, digest))) return rc;
     if ((rc = upload(&f.d_ent_idx, e_idx))) return rc;
     if ((rc = upload(&f.d_ent_hash, e_hash))) return rc;
     if ((rc = upload(&f.d_coarse, coarse))) return rc;
+    filter_bitmap_kernel<<<(f.nent + 255) / 256, 256>>>(f.d_bitmap, f.d_ent_idx, f.nent);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(0));  // plans are used on arbitrary streams afterwards
+    g_launches++;
     if ((rc = upload(&f.d_ent_slot, e_slot))) return rc;
     if ((rc = upload(&f.d_ent_piece, e_piece))) return rc;
     if ((rc = upload(&f.d_fp_id, fp_id))) return rc;

@@ -260,6 +260,12 @@ __global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const __gri
     filter_flush(a, stg);
 }
 
+// plan construction: the seed bitmap (up to 16 MiB) is built on the device from the sorted entry indices
+__global__ void __launch_bounds__(256) filter_bitmap_kernel(uint32_t *bitmap, const uint32_t *__restrict__ ent_idx, int nent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nent) atomicOr(bitmap + (ent_idx[i] >> 5), 1u << (ent_idx[i] & 31));
+}
+
 // canonical witness: no (piece', shift') < (piece, shift) whose seed occurs inside the window
 __device__ __forceinline__ bool filter_is_canonical(const uint8_t *P, const uint8_t *W, int m, int k, int s, int piece, int dk) {
     for (int i2 = 0; i2 <= piece; ++i2) {

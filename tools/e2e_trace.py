@@ -12,6 +12,8 @@ t = torch.empty(n, dtype=torch.uint8, device=dev)
 apm_b200.synth_text_device(t.data_ptr(), TEXT_SEED, 0, n)
 host = torch.empty(n, dtype=torch.uint8).pin_memory(); host.copy_(t); torch.cuda.synchronize()
 pats, _, _ = make_patterns(TEXT_SEED, 1 << 34, 4096, 64, 7)
+if len(sys.argv) > 1:
+    apm_b200.set_option("mode", sys.argv[1])
 for i in range(3):
     t0 = time.perf_counter()
     apm_b200.count_matches_ptr(host.data_ptr(), n, pats, 4)
