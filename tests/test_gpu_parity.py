@@ -754,3 +754,14 @@ def test_cli_pattern_file_positions_and_info(tmp_path):
     r = subprocess.run([apm_b200.CLI_PATH, "1", str(f)], capture_output=True, text=True,
                        env=dict(os.environ, APM_PATTERN_FILE=str(pf)), check=True)
     assert sum(l.startswith("Number of matches") for l in r.stdout.splitlines()) == len(case["patterns"]) - 1
+
+
+def test_adversarial_inputs_all_modes_agree_with_the_dp_kernel():
+    """tools/stress_modes.py: tiny alphabets, periodic / run-length / self-copying texts, indels at piece borders,
+    k <= 12: filter (also with an overflowing candidate buffer), band and direct mode == explicit-DP kernel, counts
+    and positions."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([os.sys.executable, os.path.join(root, "tools", "stress_modes.py"), "60", "20261018"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "60 cases, 0 mismatches" in r.stdout
