@@ -262,7 +262,7 @@ int upload(T **dptr, const std::vector<T> &h) {
 }  // namespace
 
 struct apm_plan {
-    int device = 0, P = 0, k = 0, ncodes = 0, num_sms = 0, mmax_all_patterns = 0;
+    int device = 0, P = 0, k = 0, ncodes = 0, num_sms = 0, mmax_all_patterns = 0, smem_optin = 0;
     Options opt;
     std::vector<std::string> pats;
     uint8_t code_of[256];
@@ -665,6 +665,14 @@ BandKernel pick_band(int k, int cell, int *K_out) {
     return nullptr;
 }
 
+// shared memory the band kernel needs for this list (its U rows are 2K windows wider than the direct kernel's)
+size_t band_smem_need(const apm_plan *pl, const SlicedList &l) {
+    int K = -1;
+    if (!pick_band(pl->k, 0, &K)) return (size_t)-1;
+    const int rowsU = sliced_rowsU(l.mmax + K) + 1;
+    return sliced_smem_bytes(pl->nplanes, rowsU, 4 * ((32 + 2 * K) | 1));
+}
+
 int launch_band(apm_plan *pl, SlicedList &l, SlicedArgs a, long long nwin, cudaStream_t st) {
     int K = -1;
     BandKernel fn = pick_band(pl->k, pl->opt.cell < 0 ? 0 : pl->opt.cell, &K);  // auto: the band rows are issue bound, plain LOP3 wins
@@ -726,7 +734,9 @@ int launch_sliced(apm_plan *pl, SlicedList &l, const uint8_t *d_buf, long long b
     a.c_neg1 = 0xFFFFFFFFu;
     // exact band mode: only the 2K+1 diagonals that can matter for D <= k (worth it when the band is
     // narrower than the matrix)
-    if (pl->opt.mode != MODE_DIRECT && pl->k <= kBandMaxK && 2 * pl->k + 1 < l.mmin)
+    // (and when its wider U table still fits the SM's shared memory: 8 symbols x long patterns x K >= 12 do not)
+    if (pl->opt.mode != MODE_DIRECT && pl->k <= kBandMaxK && 2 * pl->k + 1 < l.mmin &&
+        band_smem_need(pl, l) <= (size_t)pl->smem_optin)
         return launch_band(pl, l, a, lim - w0, st);
     // auto: measured on B200 (profiles/r01_quick_cell_variants.jsonl) -- the FMA-pipe variants win where the whole
     // pattern is one register block (m <= 32: 4 LOP3 + 2 IMAD, m <= 64: 4 LOP3 + 3 IMAD); register-file operand
@@ -1072,6 +1082,7 @@ int apm_plan_create(const char *const *patterns, const int *pattern_len, int nb_
     pl->k = approx_factor;
     cudaError_t e = cudaGetDevice(&pl->device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, pl->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, pl->device);
     if (e != cudaSuccess) {
         delete pl;
         return fail(APM_ECUDA, "cudaGetDevice/attribute: %s", cudaGetErrorString(e));

@@ -765,3 +765,18 @@ def test_adversarial_inputs_all_modes_agree_with_the_dp_kernel():
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "60 cases, 0 mismatches" in r.stdout
+
+
+@pytest.mark.parametrize("mode", ["band", "filter"])
+def test_band_kernel_too_wide_for_shared_memory_falls_back(mode):
+    """8 pattern symbols x m = 300 x k = 16: the band kernel's U table (rows of 32 + 2K windows) exceeds 227 KB, the
+    launcher must take the direct kernel instead (found by tools/stress_modes.py)."""
+    rng = np.random.default_rng(5)
+    alpha = np.frombuffer(b"ACGTNacg", dtype=np.uint8)
+    text = alpha[rng.integers(0, 8, size=30_000)].tobytes()
+    pats = [text[1000:1300], text[5000:5290], text[9000:9100]]
+    for k in (12, 16):
+        apm_b200.set_option("mode", "direct"); apm_b200.set_option("kernel", "dp")
+        want = apm_b200.count_matches(text, pats, k)
+        apm_b200.set_option("kernel", "auto"); apm_b200.set_option("mode", mode)
+        assert apm_b200.count_matches(text, pats, k) == want
