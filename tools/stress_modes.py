@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised cross-check of the exact shortcut modes against the explicit-DP kernel on adversarial inputs:
 tiny alphabets, periodic texts and patterns (identical seeds in several pieces, overlapping witnesses), edits near the
-piece boundaries, k up to 12, pattern lengths 8..300.  usage: stress_modes.py [cases] [seed]"""
+piece boundaries, k up to 17, pattern lengths 2..1100, every DP-cell code.  usage: stress_modes.py [cases] [seed]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "inf560-approximate-pattern-matching_b200"))
@@ -31,10 +31,11 @@ for c in range(cases):
             a, b, L = int(rng.integers(0, n - 500)), int(rng.integers(0, n - 500)), int(rng.integers(50, 400))
             text[b:b + L] = text[a:a + L]
     text = text.tobytes()
-    k = int(rng.integers(0, 13))
+    k = int(rng.integers(0, 18)) if rng.integers(0, 4) == 0 else int(rng.integers(0, 9))
     pats = []
     for _ in range(int(rng.integers(1, 8))):
-        m = int(rng.integers(max(2, k), 300))
+        m = int(rng.integers(max(2, k), 1100 if rng.integers(0, 10) == 0 else 300))
+        m = min(m, len(text) - 1)
         off = int(rng.integers(0, max(1, len(text) - m)))
         p = bytearray(text[off:off + m])
         for _ in range(int(rng.integers(0, k + 3))):
@@ -48,6 +49,7 @@ for c in range(cases):
     apm_b200.set_option("kernel", "auto")
     for mode, extra in (("filter", {}), ("filter", {"filter_cand_mb": "1"}), ("band", {}), ("direct", {})):
         apm_b200.set_option("mode", mode)
+        apm_b200.set_option("cell", str(rng.choice(["auto", "lop3", "fma3", "fma"])))
         for kk, vv in extra.items(): apm_b200.set_option(kk, vv)
         got, hits, _ = apm_b200.find_matches(text, pats, k, max_hits=1 << 22)
         for kk in extra: apm_b200.set_option(kk, "128")
