@@ -77,6 +77,18 @@ def test_no_cpu_fallback_without_device():
     assert ei.value.code == apm_b200.APM_ENODEVICE
     with pytest.raises(apm_b200.ApmError):
         apm_b200.Plan([b"ACG"], 0)
+    for mode in ("band", "filter"):  # the exact shortcut modes and the position output have no CPU path either
+        apm_b200.set_option("mode", mode)
+        try:
+            with pytest.raises(apm_b200.ApmError) as ei:
+                apm_b200.find_matches(b"ACGTACGTACGTACGT", [b"ACGTACGTAC"], 0)
+            assert ei.value.code == apm_b200.APM_ENODEVICE
+        finally:
+            apm_b200.set_option("mode", "direct")
+    # the reference's entry points by name: no device -> the error is reported and the caller's counter is untouched
+    from apm_b200 import refcompat
+    assert refcompat.device_count() == 0
+    assert refcompat.invoke_and_fetch(b"ACGTACGT", b"ACG", 0, initial=5) == 5
 
 
 def test_cli_usage_and_errors():
