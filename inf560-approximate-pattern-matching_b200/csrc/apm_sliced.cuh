@@ -417,22 +417,15 @@ __global__ void __launch_bounds__(kSlicedThreads, MC == 64 ? 3 : 4) sliced_count
 #pragma unroll
                     for (int j = 0; j < MC; ++j) { hp[j] = 0xFFFFFFFFu; hm[j] = cell_plus_second_plane<CELL>(); }  // D[0][j] - D[0][j-1] = +1
                     if (MC == 32 || nblk == 1) {
-                        // width within the last 8-column group of the block: the branch-free pipelined sweep over all
-                        // MC columns (the columns >= width run on whatever text follows and are reset below)
-                        if (width > MC - 8) sliced_sweep<MC, CELL, true, false, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
+                        if (width == MC) sliced_sweep<MC, CELL, true, false, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
                         else sliced_sweep<MC, CELL, false, false, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
                     } else if (b == 0) {
                         sliced_sweep<MC, CELL, true, false, true>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
                     } else if (b < nblk - 1) {
                         sliced_sweep<MC, CELL, true, true, true>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
                     } else {
-                        if (width > MC - 8) sliced_sweep<MC, CELL, true, true, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
+                        if (width == MC) sliced_sweep<MC, CELL, true, true, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
                         else sliced_sweep<MC, CELL, false, true, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
-                    }
-                    if (width < MC) {
-#pragma unroll
-                        for (int j = MC - 8; j < MC; ++j)  // columns >= width back to the neutral +1 (they add a constant)
-                            if (j >= width) { hp[j] = 0xFFFFFFFFu; hm[j] = cell_plus_second_plane<CELL>(); }
                     }
                     // block sum: sum_j (h+[j] + ~h-[j]) over the MC columns of the last row (unused ones add 2)
                     uint32_t acc[NL], pend[NL];
