@@ -27,7 +27,7 @@ constexpr int kFilterMinSeed = 8;
 constexpr int kFilterMaxSeed = 16;
 constexpr int kFilterMaxK = 16;  // == kBandDpMaxK (apm_dp.cuh)
 constexpr int kFilterThreads = 512;
-constexpr int kFilterPosPerThread = 16;
+constexpr int kFilterPosPerThread = 32;
 constexpr uint32_t kFilterHashB = 0x9E3779B1u;
 constexpr int kFilterSlabLog = 28;  // window starts per scan/verify round: candidates carry a 28-bit local start
 
@@ -154,8 +154,8 @@ __device__ __noinline__ void filter_hit(const FilterArgs &a, FilterStage *stg, l
     }
 }
 
-// Scan: every text position that can hold a seed of a window of [w0, w1).  A thread owns 16 consecutive
-// positions: its own 16 bytes come from one coalesced 128-bit load, the next 16 from the neighbouring lane by
+// Scan: every text position that can hold a seed of a window of [w0, w1).  A thread owns 32 consecutive
+// positions: its own 32 bytes come from two 128-bit loads, the next 16 from the neighbouring lane by
 // shuffle; rolling hash in registers.  Two-level probe: a 64 KB digest of the seed set lives in shared memory
 // (copied once per persistent CTA), so all but ~0.1 % of the positions are rejected by one LDS and only the
 // rest recompute their hash and touch the full bitmap in L2.
@@ -183,7 +183,7 @@ __host__ __device__ __forceinline__ uint32_t filter_digest_mask(uint32_t h) {
 }
 
 template <int S>
-__global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const __grid_constant__ FilterArgs a) {
+__global__ void __launch_bounds__(kFilterThreads, 2) filter_scan_kernel(const __grid_constant__ FilterArgs a) {
     extern __shared__ __align__(16) uint32_t s_digest[];
     FilterStage *stg = reinterpret_cast<FilterStage *>(reinterpret_cast<unsigned char *>(s_digest) + kFilterSmemBytes) +
                        (threadIdx.x >> 5);  // this warp's staging list
@@ -202,25 +202,32 @@ __global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const __gri
     const unsigned char *dig = reinterpret_cast<const unsigned char *>(s_digest);
     const long long stride = (long long)gridDim.x * kTile;
     long long base = base0 + (long long)blockIdx.x * kTile;
-    uint4 pre = make_uint4(0u, 0u, 0u, 0u);  // software prefetch: the next tile's bytes are requested a tile ahead
-    if (base < t_end) pre = filter_load16(a, base + (long long)threadIdx.x * kFilterPosPerThread);
+    // software prefetch: the next tile's 32 bytes per thread are requested a tile ahead
+    uint4 pre0 = make_uint4(0u, 0u, 0u, 0u), pre1 = pre0;
+    if (base < t_end) {
+        pre0 = filter_load16(a, base + (long long)threadIdx.x * kFilterPosPerThread);
+        pre1 = filter_load16(a, base + (long long)threadIdx.x * kFilterPosPerThread + 16);
+    }
     for (; base < t_end; base += stride) {
         const long long p0 = base + (long long)threadIdx.x * kFilterPosPerThread;
-        const uint4 own = pre;
-        if (base + stride < t_end) pre = filter_load16(a, p0 + stride);
-        uint4 nxt;
-        nxt.x = __shfl_down_sync(0xFFFFFFFFu, own.x, 1);
-        nxt.y = __shfl_down_sync(0xFFFFFFFFu, own.y, 1);
-        nxt.z = __shfl_down_sync(0xFFFFFFFFu, own.z, 1);
-        nxt.w = __shfl_down_sync(0xFFFFFFFFu, own.w, 1);
-        if (lane == 31) nxt = filter_load16(a, p0 + 16);
-        const uint32_t w[8] = {own.x, own.y, own.z, own.w, nxt.x, nxt.y, nxt.z, nxt.w};
+        const uint4 own0 = pre0, own1 = pre1;
+        if (base + stride < t_end) {
+            pre0 = filter_load16(a, p0 + stride);
+            pre1 = filter_load16(a, p0 + stride + 16);
+        }
+        uint4 nxt;  // the 16 bytes behind this thread's 32: the neighbouring lane's first 16
+        nxt.x = __shfl_down_sync(0xFFFFFFFFu, own0.x, 1);
+        nxt.y = __shfl_down_sync(0xFFFFFFFFu, own0.y, 1);
+        nxt.z = __shfl_down_sync(0xFFFFFFFFu, own0.z, 1);
+        nxt.w = __shfl_down_sync(0xFFFFFFFFu, own0.w, 1);
+        if (lane == 31) nxt = filter_load16(a, p0 + 32);
+        const uint32_t w[12] = {own0.x, own0.y, own0.z, own0.w, own1.x, own1.y, own1.z, own1.w, nxt.x, nxt.y, nxt.z, nxt.w};
         auto byte_at = [&](int i) -> uint32_t { return __byte_perm(w[i >> 2], 0u, 0x4440 + (i & 3)); };
         uint32_t h = 0;
 #pragma unroll
         for (int i = 0; i < S; ++i) h = h * kFilterHashB + byte_at(i);
-        // digest probe of the 16 positions (filter_digest_word / _mask); the answers are shifted into
-        // `maybe` from the top, so position i ends up at bit 16 + i
+        // digest probe of the 32 positions (filter_digest_word / _mask); the answers are shifted into `maybe` from
+        // the top, so after 32 steps position i sits at bit i
         uint32_t maybe = 0u;
 #pragma unroll
         for (int i = 0; i < kFilterPosPerThread; ++i) {
@@ -228,11 +235,10 @@ __global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const __gri
             maybe = __funnelshift_r(maybe, __funnelshift_r(word, 0u, h >> 13) & __funnelshift_r(word, 0u, h >> 8), 1);
             if (i + 1 < kFilterPosPerThread) h = h * kFilterHashB - byte_at(i) * a.bs + byte_at(i + S);  // roll by one byte
         }
-        maybe >>= 16;
         // positions outside [t_begin, t_end) do not count
         const long long lo = t_begin - p0, hi = t_end - p0;
-        if (lo > 0) maybe &= lo >= 16 ? 0u : ~((1u << (int)lo) - 1u);
-        if (hi < 16) maybe &= hi <= 0 ? 0u : ((1u << (int)hi) - 1u);
+        if (lo > 0) maybe &= lo >= 32 ? 0u : ~((1u << (int)lo) - 1u);
+        if (hi < 32) maybe &= hi <= 0 ? 0u : ((1u << (int)hi) - 1u);
         // ~0.1 % of the positions pass the digest.  They are queued per warp and probed 32 at a time with all
         // lanes busy (probing inline would stall the whole warp behind one lane's dependent loads).
         while (maybe) {
