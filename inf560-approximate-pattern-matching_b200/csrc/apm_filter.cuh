@@ -8,13 +8,16 @@
 //   (p, j) can match  ==>  some piece i of p has its seed at text position j + o_i + d, |d| <= k, inside W
 //
 // with o_i = floor(i * m / (k + 1)).  The scan kernel computes a rolling hash of every s-byte text substring (one
-// pass over the text, independent of the number of patterns), probes a bitmap of all seed hashes (L2 resident),
-// and for the rare hits looks the seed up, compares the bytes and emits the (pattern, window, piece, shift)
-// candidates.  The verify kernel evaluates the banded DP |row - col| <= k of src/utils.c:76-99 for each
-// candidate -- exact for the decision D <= k -- and counts a matching window only from its CANONICAL witness (the
-// lexicographically smallest (piece, shift) whose seed occurs), so a window witnessed several times is counted
-// once.  No sort, no host round trip.  If the candidate buffer overflows (low-complexity text) a flag makes the
-// verify kernel a no-op and switches on the band kernel for the same patterns and windows instead: always exact.
+// pass over the text, independent of the number of patterns) and probes a 64 KB one-word Bloom digest of all seed
+// hashes in shared memory; the ~0.1 % of the positions that pass are queued per warp and, 32 at a time, re-hashed,
+// checked against the full seed bitmap (L2), looked up through a directory, byte-compared and turned into
+// (pattern, window, piece, shift) candidates (staged per warp, one global atomic per flush).  The verify kernels
+// evaluate the banded DP |row - col| <= k of src/utils.c:76-99 for each candidate -- exact for the decision D <= k;
+// one thread per candidate for the first 32 rows, a whole warp for the few that survive -- and count a matching
+// window only from its CANONICAL witness (the lexicographically smallest (piece, shift) whose seed occurs), so a
+// window witnessed several times is counted once.  No sort, no host round trip.  If the candidate buffer
+// overflows (low-complexity text) a flag makes the verify kernels no-ops and switches on the band kernel for the
+// same patterns and windows instead: always exact.
 //
 // Work: O(text bytes) + O(candidates * m * (2k+1)) instead of O(text bytes * patterns * m * (2k+1)).
 #pragma once
