@@ -29,6 +29,7 @@
 #include "apm_sliced.cuh"
 #include "apm_band.cuh"
 #include "apm_filter.cuh"
+#include "apm_tail.cuh"
 #include "apm_util_kernels.cuh"
 
 using namespace apm;
@@ -68,6 +69,7 @@ struct Options {
     int tile = 0;    // 0 = auto
     int variant = 0; // column-step code variant (see myers_step_fma)
     int cell = -1;   // DP-cell code of the sliced/band kernels: -1 auto, 0 = 5 LOP3, 1 = 4 LOP3 + 3 IMAD, 2 = 4 LOP3 + 2 IMAD
+    int tail = 0;    // truncated tail windows: 0 = bit-parallel kernels (apm_tail.cuh), 1 = explicit DP (apm_dp.cuh)
     int reduce = 0;  // multi-GPU count reduction: 0 auto (p2p kernel, else NCCL, else host), 1 nccl, 2 host sum, 3 p2p
     long long dp_scratch_mb = 256;
     long long text_chunk_mb = 32768;  // one-shot API: a shard larger than this is streamed through two device buffers
@@ -118,6 +120,22 @@ size_t pool_class(size_t bytes) {
     return c;
 }
 
+// hand every cached DEVICE block back to the driver (the pinned staging buffers stay: an ingest may be using them)
+void release_device_cache() {
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto &kv : g_pool.free_blocks) {
+        if (kv.second.empty()) continue;
+        cudaSetDevice(kv.first.first);
+        for (void *p : kv.second) cudaFree(p);
+        kv.second.clear();
+    }
+    g_pool.free_blocks.clear();
+    g_pool.cached_bytes = 0;
+    cudaSetDevice(cur);
+}
+
 cudaError_t dev_alloc(void **p, size_t bytes) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -137,7 +155,7 @@ cudaError_t dev_alloc(void **p, size_t bytes) {
     e = cudaMalloc(p, cls);
     if (e != cudaSuccess) {  // give the cache back to the driver and retry once
         cudaGetLastError();
-        apm_release_cache();
+        release_device_cache();
         e = cudaMalloc(p, cls);
     }
     if (e == cudaSuccess) {
@@ -175,6 +193,25 @@ void dev_free(void *p) {
     }
     g_pool.free_blocks[{dev, cls}].push_back(p);
     g_pool.cached_bytes += cls;
+}
+
+// ---- dynamic shared-memory opt-in --------------------------------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (kernel, device) pair, not to a plan: two live plans
+// using the same instantiation with different sizes must not lower it under each other.  One process-wide table
+// keeps the maximum ever requested per (device, kernel) and only ever raises it.
+std::mutex g_smem_mu;
+std::map<std::pair<int, const void *>, size_t> g_smem_set;
+template <typename Fn>
+cudaError_t ensure_dyn_smem(Fn fn, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_smem_mu);
+    size_t &cur = g_smem_set[{dev, (const void *)fn}];
+    if (bytes <= cur) return cudaSuccess;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
 }
 
 // ---- kernel dispatch table ------------------------------------------------------------------------
@@ -215,8 +252,6 @@ struct Bucket {
     uint32_t *d_peq = nullptr;
     int *d_group_m = nullptr, *d_group_pat = nullptr;
     MyersKernel fn = nullptr;
-    size_t smem_set = 0;
-    int occ_cache_smem = -1, occ_cache = 0;
 };
 
 // patterns handled by the window-sliced kernel: one list for m <= 32 (MC = 32) and one for longer ones
@@ -229,7 +264,6 @@ struct SlicedList {
     uint2 *d_vscratch = nullptr;  // boundary deltas between column blocks (only when mmax > MC)
     unsigned long long *d_work = nullptr;  // item dispenser of the persistent kernel
     size_t vscratch_bytes = 0;
-    size_t smem_set[3] = {0, 0, 0};
 };
 
 
@@ -276,8 +310,9 @@ struct apm_plan {
     std::vector<SlicedList> fb_sliced;
     int nplanes = 0;
     uint8_t *d_plane_of = nullptr;
-    std::vector<int> tail_list, all_list;
-    int tail_width = 0, tail_mmax = 0, all_mmax = 0;
+    std::vector<int> tail_list, all_list;  // tail_list: patterns with m <= 256 first, then the longer ones
+    int tail_nshort = 0;                   // patterns of tail_list served by the thread-per-window tail kernel
+    int tail_width = 0, tail_mmax = 0, all_mmax = 0, tail_width_short = 0;
     uint8_t *d_code_of = nullptr, *d_pat_bytes = nullptr;
     long long *d_pat_off = nullptr;
     int *d_pat_len = nullptr, *d_tail_list = nullptr, *d_all_list = nullptr;
@@ -520,6 +555,17 @@ int build_work(apm_plan *pl) {
             pl->tail_mmax = std::max(pl->tail_mmax, m);
         }
     }
+    // thread-per-window tail kernel for m <= 256 (<= 8 words), warp-per-window for the longer ones
+    std::stable_partition(pl->tail_list.begin(), pl->tail_list.end(),
+                          [&](int p) { return (int)pl->pats[p].size() <= 32 * kTailThreadMaxWords; });
+    pl->tail_nshort = 0;
+    pl->tail_width_short = 0;
+    for (int p : pl->tail_list) {
+        const int m = (int)pl->pats[p].size();
+        if (m > 32 * kTailThreadMaxWords) break;
+        pl->tail_nshort++;
+        pl->tail_width_short = std::max(pl->tail_width_short, m - 1 - pl->k);
+    }
     int rc;
     if ((rc = build_lists(pl, main_ids, pl->buckets, pl->sliced))) return rc;
     if (!filter_ids.empty()) {
@@ -563,10 +609,7 @@ int launch_myers(apm_plan *pl, Bucket &b, const uint8_t *d_buf, long long buf_le
 
     int gpc = std::min(b.ngroups, gpc_max);
     size_t smem = myers_smem_bytes(tile, b.mmax, gpc, pl->ncodes, b.R, b.NW);
-    if (smem > b.smem_set) {
-        CUDA_TRY(cudaFuncSetAttribute(b.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        b.smem_set = smem;
-    }
+    CUDA_TRY(ensure_dyn_smem(b.fn, smem));
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, b.fn, kThreads, smem));
     if (occ < 1) return fail(APM_ECUDA, "myers kernel NW=%d R=%d does not fit an SM (smem %zu)", b.NW, b.R, smem);
@@ -609,10 +652,7 @@ int launch_sliced_mc(apm_plan *pl, SlicedList &l, SlicedArgs a, long long nwin, 
     const long long ntiles = (nwin + kSlicedTile - 1) / kSlicedTile;
     const int rowsU = sliced_rowsU(l.mmax);
     const size_t smem = sliced_smem_bytes(pl->nplanes, rowsU);
-    if (smem > l.smem_set[CELL]) {
-        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        l.smem_set[CELL] = smem;
-    }
+    CUDA_TRY(ensure_dyn_smem(fn, smem));
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kSlicedThreads, smem));
     if (occ < 1) return fail(APM_ECUDA, "sliced kernel MC=%d does not fit an SM (smem %zu)", MC, smem);
@@ -681,7 +721,7 @@ int launch_band(apm_plan *pl, SlicedList &l, SlicedArgs a, long long nwin, cudaS
     const int row_cols = 32 + 2 * K;
     const int row_bytes = 4 * (row_cols | 1);      // odd number of words: conflict-free LDS.32 across lanes
     const size_t smem = sliced_smem_bytes(pl->nplanes, rowsU, row_bytes);
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ensure_dyn_smem(fn, smem));
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kSlicedThreads, smem));
     if (occ < 1) return fail(APM_ECUDA, "band kernel K=%d does not fit an SM (smem %zu)", K, smem);
@@ -754,12 +794,9 @@ int launch_sliced(apm_plan *pl, SlicedList &l, const uint8_t *d_buf, long long b
 // gated on the round's overflow flag (they run only when the candidate buffer was too small).  Stream ordered.
 template <int S>
 cudaError_t launch_filter_scan(const FilterArgs &a, unsigned blocks, cudaStream_t st, int device) {
-    static std::atomic<bool> attr_set[64];  // 64 KB of dynamic shared memory needs the opt-in once per kernel and device
-    if (device < 0 || device >= 64 || !attr_set[device].load()) {
-        const cudaError_t e = cudaFuncSetAttribute(filter_scan_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFilterSmemBytes + (int)sizeof(FilterStage) * (kFilterThreads / 32));
-        if (e != cudaSuccess) return e;
-        if (device >= 0 && device < 64) attr_set[device].store(true);
-    }
+    (void)device;
+    const cudaError_t e = ensure_dyn_smem(filter_scan_kernel<S>, kFilterSmemBytes + sizeof(FilterStage) * (kFilterThreads / 32));
+    if (e != cudaSuccess) return e;
     filter_scan_kernel<S><<<blocks, kFilterThreads, kFilterSmemBytes + sizeof(FilterStage) * (kFilterThreads / 32), st>>>(a);
     return cudaGetLastError();
 }
@@ -853,31 +890,56 @@ int launch_dp(apm_plan *pl, const uint8_t *d_buf, long long buf_offset, long lon
     a.sink.base = 0;  // the DP kernels work on global window starts
 
     // ---- truncated tail windows of the bit-parallel patterns
-    if (!pl->tail_list.empty() && pl->tail_width > 0) {
-        const long long tail_first = std::max<long long>(0, n_total - pl->tail_mmax + 1);
-        if (j_end > tail_first && j_end > j_begin) {
-            const size_t per_thread = (size_t)(pl->tail_mmax + 1) * 4;
-            long long max_threads = std::max<long long>(pl->tail_width, (long long)(budget / per_thread));
-            int pats_per_launch = (int)std::max<long long>(1, max_threads / pl->tail_width);
-            for (size_t p0 = 0; p0 < pl->tail_list.size(); p0 += pats_per_launch) {
-                const int np = (int)std::min<size_t>(pats_per_launch, pl->tail_list.size() - p0);
-                const long long threads = (long long)np * pl->tail_width;
-                const unsigned blocks = (unsigned)((threads + 127) / 128);
-                const long long stride = (long long)blocks * 128;
-                const bool banded = pl->opt.mode != MODE_DIRECT && pl->k <= kBandDpMaxK;
-                int rc = banded ? APM_OK : ensure_scratch(pl, (size_t)stride * per_thread);
-                if (rc) return rc;
-                a.pat_list = pl->d_tail_list + p0;
-                a.npat = np;
-                a.tail_width = pl->tail_width;
-                a.scratch = pl->d_scratch;
-                a.scratch_stride = stride;
-                // direct mode: every cell of the (truncated) window; band / filter mode: only the band that decides
-                if (banded) dp_tail_band_kernel<<<blocks, 128, 0, st>>>(a);
-                else dp_tail_kernel<<<blocks, 128, 0, st>>>(a);
-                CUDA_TRY(cudaGetLastError());
-                g_launches++;
-            }
+    const long long tail_first = std::max<long long>(0, n_total - pl->tail_mmax + 1);
+    const bool have_tail = !pl->tail_list.empty() && pl->tail_width > 0 && j_end > tail_first && j_end > j_begin;
+    if (have_tail && pl->opt.tail == 0) {
+        // bit-parallel (apm_tail.cuh): s column steps per window of size s instead of s^2 cells; exact in every mode
+        TailArgs ta;
+        ta.d = a;
+        ta.code_of = pl->d_code_of;
+        ta.ncodes = pl->ncodes;
+        if (pl->tail_nshort > 0) {
+            ta.d.pat_list = pl->d_tail_list;
+            ta.d.npat = pl->tail_nshort;
+            ta.chunks = (pl->tail_width_short + kTailThreads - 1) / kTailThreads;
+            tail_myers_kernel<<<(unsigned)(pl->tail_nshort * ta.chunks), kTailThreads, 0, st>>>(ta);
+            CUDA_TRY(cudaGetLastError());
+            g_launches++;
+        }
+        const int nlong = (int)pl->tail_list.size() - pl->tail_nshort;
+        if (nlong > 0) {
+            constexpr int kWarps = kTailWarpThreads / 32;
+            ta.d.pat_list = pl->d_tail_list + pl->tail_nshort;
+            ta.d.npat = nlong;
+            ta.chunks = (pl->tail_width + kWarps - 1) / kWarps;
+            const long long blocks = (long long)nlong * ta.chunks;
+            if (blocks > 0x7FFFFFFFll) return fail(APM_EINVAL, "too many long patterns for one tail launch");
+            tail_myers_warp_kernel<<<(unsigned)blocks, kTailWarpThreads, (size_t)pl->ncodes * 32 * sizeof(uint32_t), st>>>(ta);
+            CUDA_TRY(cudaGetLastError());
+            g_launches++;
+        }
+    } else if (have_tail) {
+        const size_t per_thread = (size_t)(pl->tail_mmax + 1) * 4;
+        long long max_threads = std::max<long long>(pl->tail_width, (long long)(budget / per_thread));
+        int pats_per_launch = (int)std::max<long long>(1, max_threads / pl->tail_width);
+        for (size_t p0 = 0; p0 < pl->tail_list.size(); p0 += pats_per_launch) {
+            const int np = (int)std::min<size_t>(pats_per_launch, pl->tail_list.size() - p0);
+            const long long threads = (long long)np * pl->tail_width;
+            const unsigned blocks = (unsigned)((threads + 127) / 128);
+            const long long stride = (long long)blocks * 128;
+            const bool banded = pl->opt.mode != MODE_DIRECT && pl->k <= kBandDpMaxK;
+            int rc = banded ? APM_OK : ensure_scratch(pl, (size_t)stride * per_thread);
+            if (rc) return rc;
+            a.pat_list = pl->d_tail_list + p0;
+            a.npat = np;
+            a.tail_width = pl->tail_width;
+            a.scratch = pl->d_scratch;
+            a.scratch_stride = stride;
+            // direct mode: every cell of the (truncated) window; band / filter mode: only the band that decides
+            if (banded) dp_tail_band_kernel<<<blocks, 128, 0, st>>>(a);
+            else dp_tail_kernel<<<blocks, 128, 0, st>>>(a);
+            CUDA_TRY(cudaGetLastError());
+            g_launches++;
         }
     }
     // ---- patterns evaluated entirely by the DP kernel (too long for the bit-parallel kernel, or
@@ -928,22 +990,12 @@ extern "C" {
 
 const char *apm_last_error(void) { return tl_err.c_str(); }
 int apm_release_cache(void) {
+    release_device_cache();
     std::lock_guard<std::mutex> lk(g_pool.mu);
-    int cur = 0;
-    cudaGetDevice(&cur);
-    for (auto &kv : g_pool.free_blocks) {
-        if (kv.second.empty()) continue;
-        cudaSetDevice(kv.first.first);
-        for (void *p : kv.second) cudaFree(p);
-        kv.second.clear();
-    }
-    g_pool.free_blocks.clear();
-    g_pool.cached_bytes = 0;
     for (int i = 0; i < 2; ++i) {
         if (g_pool.pinned[i]) cudaFreeHost(g_pool.pinned[i]);
         g_pool.pinned[i] = nullptr;
     }
-    cudaSetDevice(cur);
     return APM_OK;
 }
 
@@ -1015,6 +1067,10 @@ int apm_set_option(const char *key, const char *value) {
         else if (v == "fma3") g_opt.cell = 1;
         else if (v == "fma" || v == "fma2") g_opt.cell = 2;
         else return bad();
+    } else if (k == "tail") {
+        if (v == "auto" || v == "bitpar") g_opt.tail = 0;
+        else if (v == "dp") g_opt.tail = 1;
+        else return bad();
     } else if (k == "reduce") {
         if (v == "auto") g_opt.reduce = 0;
         else if (v == "nccl") g_opt.reduce = 1;
@@ -1056,6 +1112,7 @@ const char *apm_get_option(const char *key) {
     else if (k == "tile") tl_optbuf = o.tile ? std::to_string(o.tile) : "auto";
     else if (k == "variant") tl_optbuf = std::to_string(o.variant);
     else if (k == "cell") tl_optbuf = o.cell == 2 ? "fma" : (o.cell == 1 ? "fma3" : (o.cell == 0 ? "lop3" : "auto"));
+    else if (k == "tail") tl_optbuf = o.tail == 1 ? "dp" : "bitpar";
     else if (k == "reduce") tl_optbuf = o.reduce == 1 ? "nccl" : (o.reduce == 2 ? "host" : (o.reduce == 3 ? "p2p" : "auto"));
     else if (k == "text_chunk_mb") tl_optbuf = std::to_string(o.text_chunk_mb);
     else if (k == "filter_cand_mb") tl_optbuf = std::to_string(o.filter_cand_mb);
@@ -1130,6 +1187,9 @@ int apm_plan_create(const char *const *patterns, const int *pattern_len, int nb_
         return cleanup_fail(APM_ECUDA);
     }
     if ((rc = build_work(pl))) return cleanup_fail(rc);
+    // the tables and the zeroed counters were written on the legacy stream; the plan is used on arbitrary
+    // (non-blocking) streams afterwards
+    if (cudaStreamSynchronize(0) != cudaSuccess) return cleanup_fail(fail(APM_ECUDA, "cudaStreamSynchronize failed after the plan uploads"));
     *plan_out = pl;
     return APM_OK;
 }
@@ -1160,7 +1220,10 @@ int apm_plan_set_pattern_shard(apm_plan *pl, int rank, int world) {
     CUDA_TRY(cudaDeviceSynchronize());
     pl->shard_rank = rank;
     pl->shard_world = world;
-    return build_work(pl);
+    const int rc = build_work(pl);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return APM_OK;
 }
 
 int apm_plan_set_hit_buffer(apm_plan *pl, unsigned long long *d_hits, unsigned long long capacity,
@@ -1375,6 +1438,7 @@ struct DevJob {
 void release_jobs(std::vector<DevJob> &jobs, int restore_dev) {
     for (auto &j : jobs) {
         cudaSetDevice(j.dev);
+        if (j.copy_st) cudaStreamSynchronize(j.copy_st);  // an in-flight H2D copy must not outlive its target block
         if (j.st) cudaStreamSynchronize(j.st);
         if (j.plan) apm_plan_destroy(j.plan);
         if (j.d_text) dev_free(j.d_text);
@@ -1584,34 +1648,35 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
     // ---- combine the per-GPU count vectors
     bool reduced_on_device = false;
     if (G > 1 && (opt.reduce == 0 || opt.reduce == 3)) {
-        // our own kernel over NVLink peer memory: GPU g adds its vector into GPU 0's with system-scope atomics
+        // our own kernel over NVLink peer memory: GPU 0 pulls every other GPU's vector and adds it to its own
         bool peers = true;
         for (int g = 1; g < G && peers; ++g) {
             int can = 0;
-            peers = cudaDeviceCanAccessPeer(&can, jobs[g].dev, jobs[0].dev) == cudaSuccess && can;
+            peers = cudaDeviceCanAccessPeer(&can, jobs[0].dev, jobs[g].dev) == cudaSuccess && can;
         }
         if (peers) {
             for (int g = 1; g < G; ++g) {
+                cudaEvent_t ev = nullptr;
                 cudaSetDevice(jobs[g].dev);
-                const cudaError_t pe = cudaDeviceEnablePeerAccess(jobs[0].dev, 0);
-                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
-                    return bail(fail(APM_ECUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", jobs[g].dev, jobs[0].dev, cudaGetErrorString(pe)));
-                cudaGetLastError();
-                peer_accumulate_kernel<<<(nb_patterns + 255) / 256, 256, 0, jobs[g].st>>>(jobs[g].plan->d_counts,
-                                                                                        jobs[0].plan->d_counts, nb_patterns);
-                g_launches++;
-                cudaEvent_t ev;
-                cudaError_t e = cudaGetLastError();
-                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                if (e == cudaSuccess) e = cudaEventRecord(ev, jobs[g].st);  // behind GPU g's count kernels
+                cudaSetDevice(jobs[0].dev);
                 if (e == cudaSuccess) {
-                    e = cudaEventRecord(ev, jobs[g].st);
-                    if (e == cudaSuccess) {
-                        cudaSetDevice(jobs[0].dev);
-                        e = cudaStreamWaitEvent(jobs[0].st, ev, 0);  // GPU 0 reads its vector after every contribution
+                    e = cudaDeviceEnablePeerAccess(jobs[g].dev, 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+                        cudaGetLastError();
+                        e = cudaSuccess;
                     }
-                    cudaEventDestroy(ev);
                 }
-                if (e != cudaSuccess) return bail(fail(APM_ECUDA, "peer reduction: %s", cudaGetErrorString(e)));
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(jobs[0].st, ev, 0);
+                if (e == cudaSuccess) {
+                    peer_gather_add_kernel<<<(nb_patterns + 255) / 256, 256, 0, jobs[0].st>>>(jobs[0].plan->d_counts,
+                                                                                            jobs[g].plan->d_counts, nb_patterns);
+                    e = cudaGetLastError();
+                    g_launches++;
+                }
+                if (ev) cudaEventDestroy(ev);
+                if (e != cudaSuccess) return bail(fail(APM_ECUDA, "peer reduction (%d <- %d): %s", jobs[0].dev, jobs[g].dev, cudaGetErrorString(e)));
             }
             reduced_on_device = true;
         } else if (opt.reduce == 3) {

@@ -102,16 +102,16 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters,
     if (x == 0x12345678u) out[0] = x;  // practically never true; keeps the chains alive
 }
 
-// Sum of a GPU's count vector into another GPU's vector over NVLink peer memory: system-scope atomics on the
-// mapped peer pointer, one launch per contributing GPU on its own count stream.  Replaces the MPI_Send/MPI_Recv of
-// per-pattern ints of the reference (patterns_over_ranks.c:195,389; database_over_ranks.c:179,573) in the
-// single-process multi-GPU path: no communicator, no staging buffer, the transfer is the kernel's own stores.
-__global__ void __launch_bounds__(256) peer_accumulate_kernel(const unsigned long long *__restrict__ local,
-                                                              unsigned long long *peer, int n) {
+// Single-process multi-GPU count reduction over NVLink peer memory: GPU 0 PULLS the count vector of every other GPU
+// through its mapped peer pointer and adds it to its own, one launch per contributing GPU on GPU 0's count stream
+// (which first waits for an event recorded behind that GPU's count kernels).  Plain loads from peer memory and
+// plain local adds in stream order: no cross-device atomics, so it does not depend on native peer-atomic support
+// and never mixes device- and system-scope atomics on one address.  Replaces the MPI_Send/MPI_Recv of per-pattern
+// ints of the reference (patterns_over_ranks.c:195,389; database_over_ranks.c:179,573).
+__global__ void __launch_bounds__(256) peer_gather_add_kernel(unsigned long long *__restrict__ local,
+                                                              const unsigned long long *__restrict__ peer, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long v = local[i];
-    if (v) atomicAdd_system(peer + i, v);
+    if (i < n) local[i] += peer[i];
 }
 
 // integer instructions per thread per loop iteration of int_peak_kernel<KIND>
