@@ -30,6 +30,7 @@
 #include "apm_band.cuh"
 #include "apm_filter.cuh"
 #include "apm_tail.cuh"
+#include "apm_dna.h"
 #include "apm_util_kernels.cuh"
 
 using namespace apm;
@@ -69,6 +70,7 @@ struct Options {
     int tile = 0;    // 0 = auto
     int variant = 0; // column-step code variant (see myers_step_fma)
     int cell = -1;   // DP-cell code of the sliced/band kernels: -1 auto, 0 = 5 LOP3, 1 = 4 LOP3 + 3 IMAD, 2 = 4 LOP3 + 2 IMAD
+    int filter_scan = 0;  // mode=filter: 0 auto (2-bit DNA scan when the patterns allow it), 1 hashed scan, 2 DNA scan
     int tail = 0;    // truncated tail windows: 0 = bit-parallel kernels (apm_tail.cuh), 1 = explicit DP (apm_dp.cuh)
     int reduce = 0;  // multi-GPU count reduction: 0 auto (p2p kernel, else NCCL, else host), 1 nccl, 2 host sum, 3 p2p
     long long dp_scratch_mb = 256;
@@ -282,6 +284,8 @@ struct FilterSet {
     uint64_t *d_long = nullptr;           // long-lived candidates (finished by whole warps)
     unsigned long long long_cap = 0;
     unsigned long long *d_ctr = nullptr;  // [0] candidates, [1] (low word) overflow flag, [2] long-lived candidates
+    bool use_dna = false;                 // 2-bit q-gram scan + seed-hit verification (apm_dna.cuh) instead of the hashed scan
+    DnaSet dna;
 };
 
 template <typename T>
@@ -294,6 +298,11 @@ int upload(T **dptr, const std::vector<T> &h) {
 }
 
 }  // namespace
+
+namespace apm {
+cudaError_t pool_alloc(void **p, size_t bytes) { return dev_alloc(p, bytes); }
+void pool_free(void *p) { dev_free(p); }
+}  // namespace apm
 
 struct apm_plan {
     int device = 0, P = 0, k = 0, ncodes = 0, num_sms = 0, mmax_all_patterns = 0, smem_optin = 0;
@@ -358,6 +367,7 @@ void free_work(apm_plan *pl) {
     dev_free(f.d_cand);
     dev_free(f.d_ctr);
     dev_free(f.d_long);
+    dna_free(&f.dna);
     f = FilterSet();
     dev_free(pl->d_tail_list);
     dev_free(pl->d_all_list);
@@ -446,7 +456,8 @@ int build_lists(apm_plan *pl, const std::vector<int> &ids_in, std::vector<Bucket
     return APM_OK;
 }
 
-// Seed tables of the exact filter (apm_filter.cuh) for the patterns f.ids.
+// Seed tables of the exact filter for the patterns f.ids: the 2-bit q-gram tables of apm_dna.cuh when every pattern
+// is pure ACGT (and the q-gram bitmap stays sparse), the hashed tables of apm_filter.cuh otherwise.
 int build_filter(apm_plan *pl) {
     FilterSet &f = pl->filter;
     const int k = pl->k;
@@ -459,16 +470,6 @@ int build_filter(apm_plan *pl) {
         f.mmax = std::max(f.mmax, m);
         f.mmin = std::min(f.mmin, m);
     }
-    f.nent = (int)f.ids.size() * (k + 1);
-    int lg = 0;
-    while ((1ll << lg) < f.nent) ++lg;
-    f.hb = std::max(kFilterSmemLog + 1, std::min(27, lg + 12));  // <= 1/4096 of the bitmap set  // <= 1/512 of the bitmap set: the scan rarely leaves its fast path
-    f.bs = 1u;
-    for (int i = 0; i < f.s; ++i) f.bs *= kFilterHashB;
-    std::vector<uint32_t> digest((size_t)1 << (kFilterSmemLog - 5), 0u);
-    struct Ent { uint32_t idx, hash, slot; uint8_t piece; };
-    std::vector<Ent> ents;
-    ents.reserve((size_t)f.nent);
     std::vector<int> fp_id, fp_m;
     std::vector<long long> fp_off;
     long long off = 0;
@@ -479,11 +480,40 @@ int build_filter(apm_plan *pl) {
     }
     for (size_t slot = 0; slot < f.ids.size(); ++slot) {
         const int p = f.ids[slot];
-        const std::string &pat = pl->pats[p];
-        const int m = (int)pat.size();
         fp_id.push_back(p);
-        fp_m.push_back(m);
+        fp_m.push_back((int)pl->pats[p].size());
         fp_off.push_back(all_off[p]);
+    }
+    int rc;
+    if ((rc = upload(&f.d_fp_id, fp_id))) return rc;
+    if ((rc = upload(&f.d_fp_m, fp_m))) return rc;
+    if ((rc = upload(&f.d_fp_off, fp_off))) return rc;
+    CUDA_TRY(dev_alloc((void **)&f.d_ctr, 3 * sizeof(unsigned long long)));
+    const size_t cand_bytes = (size_t)std::max<long long>(1, pl->opt.filter_cand_mb) << 20;
+
+    int dq = 0, dh = 0;
+    f.use_dna = pl->opt.filter_scan != 1 && dna_choose(pl->pats, f.ids, k, &dq, &dh);
+    if (pl->opt.filter_scan == 2 && !f.use_dna)
+        return fail(APM_EINVAL, "filter_scan=dna requested but the patterns are not pure ACGT (or too many for a q-gram bitmap)");
+    if (f.use_dna) {
+        const int erc = dna_build(pl->pats, f.ids, k, dq, dh, pl->num_sms, cand_bytes, &f.dna);
+        if (erc) return fail(APM_ECUDA, "building the q-gram tables: %s", cudaGetErrorString((cudaError_t)erc));
+        return APM_OK;
+    }
+
+    f.nent = (int)f.ids.size() * (k + 1);
+    int lg = 0;
+    while ((1ll << lg) < f.nent) ++lg;
+    f.hb = std::max(kFilterSmemLog + 1, std::min(27, lg + 12));  // <= 1/4096 of the bitmap set: the scan rarely leaves its fast path
+    f.bs = 1u;
+    for (int i = 0; i < f.s; ++i) f.bs *= kFilterHashB;
+    std::vector<uint32_t> digest((size_t)1 << (kFilterSmemLog - 5), 0u);
+    struct Ent { uint32_t idx, hash, slot; uint8_t piece; };
+    std::vector<Ent> ents;
+    ents.reserve((size_t)f.nent);
+    for (size_t slot = 0; slot < f.ids.size(); ++slot) {
+        const std::string &pat = pl->pats[f.ids[slot]];
+        const int m = (int)pat.size();
         for (int i = 0; i <= k; ++i) {
             const int o = filter_piece_offset(i, m, k);
             const uint32_t hash = filter_hash((const uint8_t *)pat.data() + o, f.s);
@@ -503,7 +533,6 @@ int build_filter(apm_plan *pl) {
         e_slot.push_back(e.slot);
         e_piece.push_back(e.piece);
     }
-    int rc;
     // the full bitmap (2^hb bits, up to 16 MiB) is zeroed and filled on the device
     const size_t bitmap_bytes = (size_t)1 << (f.hb - 3);
     CUDA_TRY(dev_alloc((void **)&f.d_bitmap, bitmap_bytes));
@@ -518,12 +547,8 @@ int build_filter(apm_plan *pl) {
     g_launches++;
     if ((rc = upload(&f.d_ent_slot, e_slot))) return rc;
     if ((rc = upload(&f.d_ent_piece, e_piece))) return rc;
-    if ((rc = upload(&f.d_fp_id, fp_id))) return rc;
-    if ((rc = upload(&f.d_fp_m, fp_m))) return rc;
-    if ((rc = upload(&f.d_fp_off, fp_off))) return rc;
-    f.cap = (unsigned long long)std::max<long long>(1, pl->opt.filter_cand_mb) * ((1ull << 20) / sizeof(uint64_t));
+    f.cap = (unsigned long long)(cand_bytes / sizeof(uint64_t));
     CUDA_TRY(dev_alloc((void **)&f.d_cand, f.cap * sizeof(uint64_t)));
-    CUDA_TRY(dev_alloc((void **)&f.d_ctr, 3 * sizeof(unsigned long long)));
     f.long_cap = std::max<unsigned long long>(1024, f.cap / 8);
     CUDA_TRY(dev_alloc((void **)&f.d_long, f.long_cap * sizeof(uint64_t)));
     return APM_OK;
@@ -806,6 +831,36 @@ int launch_filter(apm_plan *pl, const uint8_t *d_buf, long long buf_len, long lo
     FilterSet &f = pl->filter;
     const long long lim = std::min(w1, n_end - f.mmin + 1);  // full windows only
     if (f.ids.empty() || lim <= w0) return APM_OK;
+    if (f.use_dna) {
+        // 2-bit q-gram scan + seed-hit verification (apm_dna.cuh): rounds of 2^34 window starts (35-bit positions)
+        DnaRun r;
+        r.buf = d_buf;
+        r.buf_len = buf_len;
+        r.n_end = n_end;
+        r.k = pl->k;
+        r.fp_id = f.d_fp_id;
+        r.fp_m = f.d_fp_m;
+        r.fp_off = f.d_fp_off;
+        r.pat_bytes = pl->d_pat_bytes;
+        r.ctr = f.d_ctr;
+        r.counts = pl->d_counts;
+        r.sink = pl->sink;
+        const long long round = 1ll << 34;
+        for (long long r0 = w0; r0 < lim; r0 += round) {
+            r.w0 = r0;
+            r.w1 = std::min(lim, r0 + round);
+            int nl = 0;
+            CUDA_TRY(dna_launch(f.dna, r, st, &nl));
+            g_launches += nl;
+            const unsigned int *ovf = reinterpret_cast<unsigned int *>(f.d_ctr + 1);
+            int rc;
+            for (auto &b : pl->fb_buckets)
+                if ((rc = launch_myers(pl, b, d_buf, buf_len, n_end, r.w0, r.w1, st, ovf))) return rc;
+            for (auto &l : pl->fb_sliced)
+                if ((rc = launch_sliced(pl, l, d_buf, buf_len, n_end, r.w0, r.w1, st, ovf))) return rc;
+        }
+        return APM_OK;
+    }
     FilterArgs a;
     a.buf = d_buf;
     a.buf_len = buf_len;
@@ -1067,6 +1122,11 @@ int apm_set_option(const char *key, const char *value) {
         else if (v == "fma3") g_opt.cell = 1;
         else if (v == "fma" || v == "fma2") g_opt.cell = 2;
         else return bad();
+    } else if (k == "filter_scan") {
+        if (v == "auto") g_opt.filter_scan = 0;
+        else if (v == "hash") g_opt.filter_scan = 1;
+        else if (v == "dna") g_opt.filter_scan = 2;
+        else return bad();
     } else if (k == "tail") {
         if (v == "auto" || v == "bitpar") g_opt.tail = 0;
         else if (v == "dp") g_opt.tail = 1;
@@ -1112,6 +1172,7 @@ const char *apm_get_option(const char *key) {
     else if (k == "tile") tl_optbuf = o.tile ? std::to_string(o.tile) : "auto";
     else if (k == "variant") tl_optbuf = std::to_string(o.variant);
     else if (k == "cell") tl_optbuf = o.cell == 2 ? "fma" : (o.cell == 1 ? "fma3" : (o.cell == 0 ? "lop3" : "auto"));
+    else if (k == "filter_scan") tl_optbuf = o.filter_scan == 1 ? "hash" : (o.filter_scan == 2 ? "dna" : "auto");
     else if (k == "tail") tl_optbuf = o.tail == 1 ? "dp" : "bitpar";
     else if (k == "reduce") tl_optbuf = o.reduce == 1 ? "nccl" : (o.reduce == 2 ? "host" : (o.reduce == 3 ? "p2p" : "auto"));
     else if (k == "text_chunk_mb") tl_optbuf = std::to_string(o.text_chunk_mb);

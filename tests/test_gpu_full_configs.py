@@ -98,3 +98,81 @@ def test_full_config(text_1g, name, P, m, k, submod):
             pad = b"" if end == N else b"\0" * m
             want = [oracle.count_range(seg + pad, pats[i], k, 0, L) for i in chk]
             assert got == want, (name, s)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE config 5 at FULL size: 2^34 B synthetic ACGT text x 4096 patterns (m = 64, k = 4) on one B200.
+# The complete count vector of the exact band mode over the whole text (412 s of GPU time, tools/config5_full.py,
+# profiles/r01_config5_full.json) is pinned by its sha256; here the exact filter mode recomputes the whole vector
+# in a few milliseconds and must reproduce that hash, and band mode / the oracle re-check it on sub-ranges.
+# ---------------------------------------------------------------------------------------------------------------
+CONFIG5_SHA256 = "a3f964173cd6c44b4c638930ee412798843f9e777dcc45a39345a2332c6bc3a7"
+CONFIG5_TOTAL = 19412
+
+
+@pytest.mark.parametrize("scan", ["auto", "hash"])
+def test_config5_full_size(scan):
+    import hashlib
+    import json
+
+    import torch
+    N5, P, m, k = 1 << 34, 4096, 64, 4
+    free, _ = torch.cuda.mem_get_info()
+    if free < N5 + (2 << 30):
+        pytest.skip("needs 18 GB of free device memory")
+    apm_b200.release_cache()
+    text = torch.empty(N5, dtype=torch.uint8, device="cuda")
+    apm_b200.synth_text_device(text.data_ptr(), TEXT_SEED, 0, N5)
+    torch.cuda.synchronize()
+    ptr = text.data_ptr()
+    pats, offs, nsub = make_patterns(TEXT_SEED, N5, P, m, 7)
+    W = N5 - k
+    apm_b200.set_option("mode", "filter")
+    apm_b200.set_option("filter_scan", scan)
+    try:
+        with apm_b200.Plan(pats, k) as fplan:
+            fplan.count_device(ptr, 0, N5, N5, 0, W)
+            whole = fplan.read_counts()
+            assert sum(whole) == CONFIG5_TOTAL
+            assert hashlib.sha256(json.dumps(whole).encode()).hexdigest() == CONFIG5_SHA256
+            for p in range(P):
+                if offs[p] is not None and nsub[p] <= k:
+                    assert whole[p] >= 1, p
+            # 8 database shards (the cuts of the 8-GPU run) add up to the whole, each with its own halo'd buffer view
+            fplan.zero_counts()
+            cuts = [(W * g // 8) & ~15 for g in range(8)] + [W]
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                e = min(N5, b + m - 1)
+                fplan.count_device(ptr + a, a, e - a, N5, a, b)
+            assert fplan.read_counts() == whole
+            # sub-ranges: 8 random 2^25-window ranges, every shard seam +- m, the global tail -- filter vs band
+            rng = np.random.default_rng(55)
+            ranges = [(int(a), int(a) + (1 << 25)) for a in rng.integers(0, W - (1 << 25), size=8)]
+            ranges += [(c - 4 * m, c + 4 * m) for c in cuts[1:-1]] + [(W - (1 << 20), W)]
+            fparts = []
+            for a, b in ranges:
+                fplan.zero_counts()
+                fplan.count_device(ptr, 0, N5, N5, a, b)
+                fparts.append(fplan.read_counts())
+        apm_b200.set_option("mode", "band")
+        with apm_b200.Plan(pats, k) as bplan:
+            for (a, b), fp in zip(ranges, fparts):
+                bplan.zero_counts()
+                bplan.count_device(ptr, 0, N5, N5, a, b)
+                assert bplan.read_counts() == fp, (a, b)
+        # oracle slices: the global tail, the start, the neighbourhood of planted patterns
+        apm_b200.set_option("mode", "filter")
+        L, chk = 5000, [0, 1, 2, 3, 4, P - 1]
+        with apm_b200.Plan([pats[i] for i in chk], k) as plan:
+            for s in [0, W - L] + [int(offs[i]) - 100 for i in (0, 1, 2, 3) if offs[i] is not None and offs[i] > 100]:
+                plan.zero_counts()
+                plan.count_device(ptr, 0, N5, N5, s, s + L)
+                got = plan.read_counts()
+                end = min(N5, s + L + m - 1)
+                seg = oracle.synth_text(TEXT_SEED, s, end - s).tobytes() + (b"" if end == N5 else b"\0" * m)
+                assert got == [oracle.count_range(seg, pats[i], k, 0, L) for i in chk], s
+    finally:
+        apm_b200.set_option("filter_scan", "auto")
+        apm_b200.set_option("mode", "band")
+        del text
+        torch.cuda.empty_cache()

@@ -10,6 +10,7 @@ P, m, k = (int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv
 text = torch.empty(n, dtype=torch.uint8, device="cuda")
 apm_b200.synth_text_device(text.data_ptr(), TEXT_SEED, 0, n)
 apm_b200.set_option("mode", "filter")
+apm_b200.set_option("filter_scan", os.environ.get("APM_FILTER_SCAN", "auto"))
 pats, _, _ = make_patterns(TEXT_SEED, n, P, m, 7 if m < 100 else 14)
 with apm_b200.Plan(pats, k) as plan:
     for it in range(3):
