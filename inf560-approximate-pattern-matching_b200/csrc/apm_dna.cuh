@@ -130,10 +130,12 @@ __device__ __noinline__ uint4 dna_load16(const DnaArgs &a, long long pos) {
 //     look-ups ~4x at 4096 patterns).  (b) CSR look-up of the q-gram's entries in L2 and 2-bit compare of the
 //     piece's first 16 symbols against the packed stream.  Survivors are SEED HITS; whether the text bytes are
 //     really A/C/G/T (and symbols 17.. of long pieces) is checked by the byte-exact stage-2 verification.
+template <int H>
 __device__ __forceinline__ void dna_probe(const DnaArgs &a, const uint32_t *slab, const uint32_t *s_bloom, long long base,
                                           int ts, unsigned int *s_count) {
     bool any = false;
-    for (int off = 0; off < a.h; ++off) {
+#pragma unroll
+    for (int off = 0; off < H; ++off) {
         const int tps = ts - off + 16;  // + 16: slab index 0 is the look-behind word
         const uint32_t gram = __funnelshift_r(slab[tps >> 4], slab[(tps >> 4) + 1], 2 * (tps & 15)) & a.gmask;
         const uint32_t bi = dna_bloom_index(gram);
@@ -258,11 +260,11 @@ __global__ void __launch_bounds__(kDnaThreads, 1) dna_scan_kernel(const __grid_c
                 }
                 __syncwarp();
                 const int n = min(total, kDnaQueue);
-                for (int qi = lane; qi < n; qi += 32) dna_probe(a, slab, s_bloom, base, (int)queue[qi], &s_count);
+                for (int qi = lane; qi < n; qi += 32) dna_probe<H>(a, slab, s_bloom, base, (int)queue[qi], &s_count);
                 while (rest) {  // queue full (dense bitmap): probe inline
                     const int s = __ffs(rest) - 1;
                     rest &= rest - 1u;
-                    dna_probe(a, slab, s_bloom, base, 32 * H * lane + H * s, &s_count);
+                    dna_probe<H>(a, slab, s_bloom, base, 32 * H * lane + H * s, &s_count);
                 }
             }
             __syncwarp();  // the slab and the queue are rewritten by the next iteration
