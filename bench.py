@@ -162,6 +162,116 @@ def run_reference(args) -> None:
     _emit(line)
 
 
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE configs 3 and 4 (1 GiB synthetic text): complete job in exact filter mode + direct / band slabs
+# ---------------------------------------------------------------------------------------------------
+def run_config_1gib(torch, apm_b200, dev, stream, name: str, P: int, m: int, k: int, submod: int, hbm_peak: float) -> dict:
+    from apm_b200.synth import TEXT_SEED, make_patterns
+    n = 1 << 30
+    text = torch.empty(n, dtype=torch.uint8, device=dev)
+    apm_b200.synth_text_device(text.data_ptr(), TEXT_SEED, 0, n)
+    torch.cuda.synchronize()
+    pats, offs, nsub = make_patterns(TEXT_SEED, n, P, m, submod)
+    W = n - k
+    out = {"workload": f"{name}: 2^30 B synthetic ACGT text, {P} patterns m={m}, k={k}"}
+
+    def timed(plan, a, b, reps):
+        ms = []
+        for _ in range(reps):
+            plan.zero_counts(stream)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan.count_device(text.data_ptr(), 0, n, n, a, b, stream)
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        return ms, plan.read_counts(stream)
+
+    apm_b200.set_option("mode", "filter")
+    with apm_b200.Plan(pats, k) as plan:
+        ms, whole = timed(plan, 0, W, 5)
+        fms = sum(ms[2:]) / len(ms[2:])  # the first two passes warm the tables
+        _, fsub = timed(plan, 0, 1 << 24, 1)
+    planted = [p for p in range(P) if offs[p] is not None and nsub[p] <= k]
+    out["filter_full_job"] = {"ms": fms, "text_gbs": n / (fms * 1e-3) / 1e9, "hbm_frac": n / (fms * 1e-3) / 1e9 / hbm_peak,
+                              "effective_gcups": cells_text(n, P, m, k) / (fms * 1e-3) / 1e9, "total_matches": int(sum(whole)),
+                              "planted_found": all(whole[p] >= 1 for p in planted)}
+    slab = 1 << 20
+    apm_b200.set_option("mode", "band")
+    with apm_b200.Plan(pats, k) as plan:
+        _, bsub = timed(plan, 0, 1 << 24, 1)
+        ms, bslab = timed(plan, 4 << 20, (4 << 20) + slab, 4)
+        bms = sum(ms[1:]) / len(ms[1:])
+    apm_b200.set_option("mode", "direct")
+    with apm_b200.Plan(pats, k) as plan:
+        ms, dslab = timed(plan, 4 << 20, (4 << 20) + slab, 4)
+        dms = sum(ms[1:]) / len(ms[1:])
+    out["direct_slab"] = {"gcups": cells_full(slab, P, m) / (dms * 1e-3) / 1e9, "ms": dms, "slab_windows": slab}
+    out["band_slab"] = {"effective_gcups": cells_full(slab, P, m) / (bms * 1e-3) / 1e9, "ms": bms, "slab_windows": slab}
+    out["parity"] = {"filter_eq_band_first_2p24_windows": fsub == bsub, "band_eq_direct_slab": bslab == dslab}
+    del text
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# N > 1: the multi-GPU paths that a one-GPU test box can never run
+# ---------------------------------------------------------------------------------------------------
+def multi_gpu_parity(torch, dist, apm_b200, dev, rank: int, world: int) -> dict | None:
+    """(a) every rank: one PATTERN-shard step (p % world == rank, patterns_over_ranks.c:161) + all-reduce;
+    (b) rank 0 alone: the single-process multi-GPU C path apm_count_matches(gpus=N) with database shards and
+    pattern shards, count reduction by our peer kernel (p2p) and by ncclAllReduce -- all compared with rank 0's
+    single-GPU result on a config-2-sized input (64 patterns of length 32, k = 2)."""
+    from apm_b200.synth import TEXT_SEED, make_patterns
+    import numpy as np
+    n, P, m, k = 1 << 20, 64, 32, 2
+    pats, _, _ = make_patterns(TEXT_SEED, n, P, m, 4)
+    pats = pats[:48] + [pats[0][:20], pats[1] + pats[2], pats[3] * 4, b"ACGT" * 16]  # mixed lengths: 20 .. 128
+    pats += pats[48:] * 3
+    pats = pats[:P]
+    text = torch.empty(n, dtype=torch.uint8, device=dev)
+    apm_b200.synth_text_device(text.data_ptr(), TEXT_SEED, 0, n)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+    res = {}
+    with apm_b200.Plan(pats, k) as plan:  # single GPU, everything
+        plan.count_device(text.data_ptr(), 0, n, n, 0, n, stream)
+        want = torch.tensor(plan.read_counts(stream), dtype=torch.int64, device=dev)
+    dist.broadcast(want, src=0)
+    with apm_b200.Plan(pats, k) as plan:  # (a)
+        plan.set_pattern_shard(rank, world)
+        plan.count_device(text.data_ptr(), 0, n, n, 0, n, stream)
+        part = torch.tensor(plan.read_counts(stream), dtype=torch.int64, device=dev)
+    dist.all_reduce(part, op=dist.ReduceOp.SUM)
+    ok = torch.tensor([int(bool((part == want).all().item()))], dtype=torch.int64, device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    res["pattern_shard_allreduce"] = "ok" if int(ok.item()) == 1 else "MISMATCH"
+    dist.barrier()
+    if rank == 0:  # (b) the other ranks idle at the barrier below
+        host = text.cpu().numpy().tobytes()
+        w = want.cpu().tolist()
+        apm_b200.set_option("gpus", str(world))
+        try:
+            for name, shard, reduce in (("single_process_db_p2p", "db", "p2p"), ("single_process_db_nccl", "db", "nccl"),
+                                        ("single_process_patterns_p2p", "patterns", "p2p"),
+                                        ("single_process_patterns_host", "patterns", "host")):
+                apm_b200.set_option("shard", shard)
+                apm_b200.set_option("reduce", reduce)
+                try:
+                    got = apm_b200.count_matches(host, pats, k)
+                    res[name] = "ok" if got == w else "MISMATCH"
+                except apm_b200.ApmError as e:
+                    res[name] = f"error: {e}"
+        finally:
+            apm_b200.set_option("gpus", "1")
+            apm_b200.set_option("shard", "auto")
+            apm_b200.set_option("reduce", "auto")
+            apm_b200.set_device(dev.index)
+    dist.barrier()
+    del text
+    return res if rank == 0 else None
+
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
@@ -334,6 +444,7 @@ def run_ours(args) -> None:
            "d2h_bytes_per_step": 8 * NB_PATTERNS, "ms_per_step": e2e_dt * 1e3,
            "call": "apm_count_matches(host text slab + halo, 4096 patterns, k=4): plan build + H2D + kernels + D2H"}
 
+    mgp = multi_gpu_parity(torch, dist, apm_b200, dev, rank, world) if world > 1 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -365,23 +476,35 @@ def run_ours(args) -> None:
     except Exception:
         pass
     algorithmic_bytes = slab + (M - 1) + NB_PATTERNS * (M + 16) + 8 * NB_PATTERNS  # text + halo + patterns + counts
+    # what the window-sliced kernel EXECUTES per unit (pattern, window): cell = 4 LOP3 (ALU pipe) + 3 IMAD (FMA pipe)
+    # per 32 windows for m = 64; the Myers kernel executes the algorithmic 10 ops per word step
+    units_per_s = float(slab) * NB_PATTERNS / (ms_step * 1e-3)
+    sliced = args.kernel in ("auto", "sliced")
+    lop3_per_unit = 4.0 * M * M / 32 if sliced else 7.0 * M * ((M + 31) // 32)
+    exec_per_unit = 7.0 * M * M / 32 if sliced else 10.0 * M * ((M + 31) // 32)
     roofline = {
         "bound": "int_alu", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tiop/s",
-        "frac": achieved / int_peak, "traffic": traffic, "algorithmic_bytes": algorithmic_bytes,
+        "frac": achieved / int_peak, "frac_executed": exec_per_unit * units_per_s / int_peak,
+        "alu_pipe_frac": lop3_per_unit * units_per_s / peak1,
+        "executed_ops_per_unit": exec_per_unit, "alu_pipe_ops_per_unit": lop3_per_unit,
+        "traffic": traffic, "traffic_source": "static: profiles/traffic.json, ncu --set full capture of this configuration "
+        "(dram__bytes_read.sum + dram__bytes_write.sum per launch); null when this slab size was not captured",
+        "algorithmic_bytes": algorithmic_bytes,
         "kernel": "sliced_count_kernel<64, 1>" if args.kernel in ("auto", "sliced") else "myers_count_kernel<2,4,0>",
         "algorithmic_ops_per_unit": "10*m*ceil(m/32) = 1280 int32 ops per (pattern, window), SURVEY.md 8d",
         "peak_source": "measured in this run: max(LOP3+IADD3, LOP3+IMAD) dependency-free microbenchmark",
         "lop3_only_peak": peak1 / 1e12,
         "note": "frac is on SURVEY's ALGORITHMIC op count (10 ops per 32-cell word step of the row-parallel "
                 "formulation). The window-sliced kernel EXECUTES fewer: 4 LOP3 (ALU pipe) + 3 IMAD (FMA pipe) per "
-                "cell and 32 windows = 512 + 384 instructions per unit, so frac can exceed 1; its own bounds are "
-                "the ALU pipe (lop3_only_peak; ncu: 81 % busy) and register-file operand bandwidth (DESIGN.md 4.1)",
+                "cell and 32 windows = 512 + 384 instructions per unit, so frac can exceed 1; frac_executed is the "
+                "same on the ops it executes (vs the LOP3+IMAD peak) and alu_pipe_frac its LOP3 rate vs lop3_only_peak, "
+                "the pipe that bounds it (DESIGN.md 4.1)",
     }
     if filt is not None:  # the filter scan reads the text exactly once: its roofline is HBM
         filt["roofline"] = {"bound": "hbm", "achieved": filt["text_gbs"], "peak": hbm_peak * world, "unit": "GB/s",
                             "frac": filt["text_gbs"] / (hbm_peak * world),
-                            "note": "whole job incl. verification, tail windows and the count all-reduce; the scan kernel "
-                                    "alone reaches ~0.9 TB/s per GPU and is instruction-issue bound (DESIGN.md 4.1c)"}
+                            "note": "whole job incl. seed-hit verification, tail windows and the count all-reduce; the "
+                                    "2-bit q-gram scan kernel alone runs at 2.6 TB/s per GPU at 4096 patterns (DESIGN.md 4.1c)"}
     roofline_hbm = {"bound": "hbm", "achieved": text_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": text_gbs / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                     "note": "text bytes per second; the path is compute bound by construction (>1e5 int ops per text byte)"}
@@ -404,6 +527,14 @@ def run_ours(args) -> None:
         gc, dt, cores, kind, sample = cpu_reference_rate(160 * 1024, 16)
         cpu = {"value": gc, "unit": "GCUPS", "cores": cores, "kind": kind, "sample": sample, "seconds": dt}
 
+    configs = None
+    if world == 1 and not args.no_configs:
+        del shard
+        torch.cuda.empty_cache()
+        apm_b200.release_cache()
+        configs = {"3": run_config_1gib(torch, apm_b200, dev, stream, "config3", 1024, 64, 4, 7, hbm_peak),
+                   "4": run_config_1gib(torch, apm_b200, dev, stream, "config4", 256, 200, 10, 14, hbm_peak)}
+
     line = {
         "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
@@ -413,6 +544,7 @@ def run_ours(args) -> None:
                    "slabs of a 16 GiB text (inputs larger than L2)", "text_bytes_per_rank": int(b1 - b0)},
         "text_gbs": text_gbs, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "parity": parity, "band_mode": band, "filter_mode": filt,
+        "configs": configs, "multi_gpu_parity": mgp,
     }
     _emit(line)
     if world > 1:
@@ -458,7 +590,9 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--kernel", choices=["auto", "sliced", "myers"], default="auto")
-    ap.add_argument("--slab-windows", type=int, default=1 << 20, help="window starts per step and rank")
+    ap.add_argument("--slab-windows", type=int, default=1 << 23,
+                    help="window starts per step and rank (2^23: 1.2 s per step, so --steps 20 times >= 20 s of windows)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config-3 / config-4 (1 GiB) measurements")
     ap.add_argument("--e2e-windows", type=int, default=1 << 20)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip cpu_baseline + parity spot check")
