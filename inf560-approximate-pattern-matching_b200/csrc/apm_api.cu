@@ -19,7 +19,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -76,6 +78,7 @@ struct Options {
     long long dp_scratch_mb = 256;
     long long text_chunk_mb = 32768;  // one-shot API: a shard larger than this is streamed through two device buffers
     long long filter_cand_mb = 128;  // candidate buffer of the seed filter (mode=filter), MiB
+    int ingest_threads = 0;  // reader threads per GPU of the chunked ingest (0 = auto: host threads / GPUs, 1..8)
     long long cache_mb = 4096;  // device memory kept for reuse between calls (dev_alloc / dev_free)
 };
 std::mutex g_opt_mu;
@@ -110,10 +113,33 @@ struct DevPool {
     std::map<std::pair<int, size_t>, std::vector<void *>> free_blocks;  // (device, class bytes) -> blocks
     std::map<void *, std::pair<int, size_t>> live;                      // block -> (device, class bytes)
     size_t cached_bytes = 0;
-    uint8_t *pinned[2] = {nullptr, nullptr};                            // file-ingest staging buffers
+    std::vector<uint8_t *> pinned_free;                                 // ingest staging buffers (kPinnedChunk each), not in use
 };
 DevPool g_pool;
-constexpr size_t kPinnedChunk = (size_t)32 << 20;
+constexpr size_t kPinnedChunk = (size_t)16 << 20;
+
+// pinned staging buffers of the chunked ingest: taken from / returned to the pool (cudaHostAlloc costs milliseconds)
+uint8_t *pinned_acquire() {
+    {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        if (!g_pool.pinned_free.empty()) {
+            uint8_t *p = g_pool.pinned_free.back();
+            g_pool.pinned_free.pop_back();
+            return p;
+        }
+    }
+    uint8_t *p = nullptr;
+    if (cudaHostAlloc((void **)&p, kPinnedChunk, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void pinned_release(uint8_t *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    g_pool.pinned_free.push_back(p);
+}
 
 size_t pool_class(size_t bytes) {
     size_t c = 512;
@@ -1047,10 +1073,8 @@ const char *apm_last_error(void) { return tl_err.c_str(); }
 int apm_release_cache(void) {
     release_device_cache();
     std::lock_guard<std::mutex> lk(g_pool.mu);
-    for (int i = 0; i < 2; ++i) {
-        if (g_pool.pinned[i]) cudaFreeHost(g_pool.pinned[i]);
-        g_pool.pinned[i] = nullptr;
-    }
+    for (uint8_t *p : g_pool.pinned_free) cudaFreeHost(p);  // buffers an ingest is using are not in this list
+    g_pool.pinned_free.clear();
     return APM_OK;
 }
 
@@ -1071,6 +1095,7 @@ int apm_set_device(int device) {
     if (rc) return rc;
     if (device < 0 || device >= n) return fail(APM_EINVAL, "device %d out of range (0..%d)", device, n - 1);
     CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaFree(nullptr));  // create the primary context now, not inside the first timed call
     return APM_OK;
 }
 
@@ -1149,6 +1174,13 @@ int apm_set_option(const char *key, const char *value) {
         long long mb = atoll(value);
         if (v.empty() || v.find_first_not_of("0123456789") != std::string::npos || mb > (1ll << 20)) return bad();
         g_opt.cache_mb = mb;
+    } else if (k == "ingest_threads") {
+        if (v == "auto") g_opt.ingest_threads = 0;
+        else {
+            int n = atoi(value);
+            if (n < 1 || n > 64) return bad();
+            g_opt.ingest_threads = n;
+        }
     } else if (k == "dp_scratch_mb") {
         long long mb = atoll(value);
         if (mb < 1 || mb > 65536) return bad();
@@ -1178,6 +1210,7 @@ const char *apm_get_option(const char *key) {
     else if (k == "text_chunk_mb") tl_optbuf = std::to_string(o.text_chunk_mb);
     else if (k == "filter_cand_mb") tl_optbuf = std::to_string(o.filter_cand_mb);
     else if (k == "cache_mb") tl_optbuf = std::to_string(o.cache_mb);
+    else if (k == "ingest_threads") tl_optbuf = o.ingest_threads ? std::to_string(o.ingest_threads) : "auto";
     else if (k == "dp_scratch_mb") tl_optbuf = std::to_string(o.dp_scratch_mb);
     else return nullptr;
     return tl_optbuf.c_str();
@@ -1520,66 +1553,154 @@ struct TextSource {
     int fd = -1;
 };
 
-// Loads the global bytes [b0, b1) into d_dst.  Host buffer: one async copy on `st`.  File: pread into two pinned
-// staging buffers (cached in the pool) + async H2D on `copy_st`, so page-cache / disk reads overlap the copies;
-// after every chunk `on_chunk(bytes_end, event)` is called with the global end of the bytes enqueued so far and
-// an event recorded behind that chunk's copy -- the caller starts counting the windows that are complete while
-// the next chunk is still being read (ingest overlapped with counting).
+// Loads the global bytes [b0, b1) into d_dst and tells the caller, chunk by chunk, how far the text has arrived.
+//
+// Small or already page-locked host buffers: one async copy.  Everything else -- files, and pageable host buffers of
+// more than a few MiB -- goes through the chunked ingest: R reader threads per GPU, each with two pinned 16 MiB
+// staging buffers and its own copy stream, take the chunks round-robin (pread from the page cache / disk, or a
+// memcpy out of the caller's pageable buffer, then cudaMemcpyAsync + an event per chunk).  The calling thread
+// consumes the chunks IN ORDER: it makes the count stream wait for the chunk's event and calls on_chunk(bytes_end),
+// which launches the counting of the windows that are complete while the readers are already several chunks ahead
+// (ingest overlapped with counting; replaces read_input_file of utils.c:12-68).
+// `wait_before`: optional event every copy stream waits for first (the target buffer is still being counted).
+struct IngestShared {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int> state;  // per chunk: 0 pending, 1 copy enqueued (its event is recorded), -1 failed
+    std::atomic<bool> abort{false};
+    std::string err;
+};
+
+int ingest_reader_count(const Options &opt, int gpus_in_flight) {
+    if (opt.ingest_threads > 0) return opt.ingest_threads;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    return (int)std::max(1u, std::min(8u, hw / (unsigned)std::max(1, gpus_in_flight)));
+}
+
+bool host_pointer_is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 extern "C++" template <typename OnChunk>
 int copy_range_to_device(const TextSource &src, long long b0, long long b1, uint8_t *d_dst, cudaStream_t st,
-                         cudaStream_t copy_st, OnChunk on_chunk) {
+                         cudaStream_t copy_st, cudaEvent_t wait_before, int readers, OnChunk on_chunk) {
     if (b1 <= b0) return APM_OK;
-    if (src.host) {  // one async copy; on the copy stream when there is one (the count stream then waits for it)
-        CUDA_TRY(cudaMemcpyAsync(d_dst, src.host + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, copy_st ? copy_st : st));
-        if (copy_st) {
-            cudaEvent_t ev;
-            CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            cudaError_t e = cudaEventRecord(ev, copy_st);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev, 0);
-            cudaEventDestroy(ev);
-            if (e != cudaSuccess) return fail(APM_ECUDA, "H2D copy: %s", cudaGetErrorString(e));
-        }
-        return APM_OK;
+    const long long total = b1 - b0;
+    if (src.host && (total <= (long long)(8 << 20) || host_pointer_is_pinned(src.host + b0))) {
+        // one async copy on the copy stream; the count stream waits for it
+        if (wait_before) CUDA_TRY(cudaStreamWaitEvent(copy_st, wait_before, 0));
+        CUDA_TRY(cudaMemcpyAsync(d_dst, src.host + b0, (size_t)total, cudaMemcpyHostToDevice, copy_st));
+        cudaEvent_t ev;
+        CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaError_t e = cudaEventRecord(ev, copy_st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev, 0);
+        cudaEventDestroy(ev);
+        if (e != cudaSuccess) return fail(APM_ECUDA, "H2D copy: %s", cudaGetErrorString(e));
+        return on_chunk(b1);
     }
-    const size_t chunk = kPinnedChunk;
-    static std::mutex ingest_mu;  // one ingest at a time per process: the staging buffers are shared
-    std::lock_guard<std::mutex> ingest_lk(ingest_mu);
-    uint8_t *pin[2] = {nullptr, nullptr};
-    cudaEvent_t done[2];
-    {
-        std::lock_guard<std::mutex> lk(g_pool.mu);
-        for (int i = 0; i < 2; ++i) {
-            if (!g_pool.pinned[i]) CUDA_TRY(cudaMallocHost((void **)&g_pool.pinned[i], chunk));
-            pin[i] = g_pool.pinned[i];
+    const long long chunk = (long long)kPinnedChunk;
+    const long long nchunks = (total + chunk - 1) / chunk;
+    const int R = (int)std::max<long long>(1, std::min<long long>(readers, nchunks));
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::vector<cudaEvent_t> events((size_t)nchunks, nullptr);
+    for (auto &ev : events)
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            for (auto &e2 : events)
+                if (e2) cudaEventDestroy(e2);
+            return fail(APM_ECUDA, "cudaEventCreate failed");
         }
-    }
-    CUDA_TRY(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
-    int rc = APM_OK, s = 0;
-    bool used[2] = {false, false};
-    for (long long pos = b0; pos < b1 && !rc; s ^= 1) {
-        const size_t want = (size_t)std::min<long long>((long long)chunk, b1 - pos);
-        if (used[s]) cudaEventSynchronize(done[s]);
-        size_t got = 0;
-        while (got < want) {
-            ssize_t r = pread(src.fd, pin[s] + got, want - got, (off_t)(pos + (long long)got));
-            if (r <= 0) {
-                rc = fail(APM_EIO, "short read at byte %lld", pos + (long long)got);
-                break;
+    IngestShared sh;
+    sh.state.assign((size_t)nchunks, 0);
+    auto reader = [&](int r) {
+        cudaStream_t rs = nullptr;
+        uint8_t *pin[2] = {nullptr, nullptr};
+        long long last[2] = {-1, -1};
+        auto failed = [&](long long c, const std::string &why) {
+            std::lock_guard<std::mutex> lk(sh.mu);
+            if (sh.err.empty()) sh.err = why;
+            sh.state[(size_t)c] = -1;
+            sh.abort = true;
+            sh.cv.notify_all();
+        };
+        bool ok = cudaSetDevice(dev) == cudaSuccess && cudaStreamCreateWithFlags(&rs, cudaStreamNonBlocking) == cudaSuccess;
+        if (ok && wait_before) ok = cudaStreamWaitEvent(rs, wait_before, 0) == cudaSuccess;
+        if (ok) {
+            pin[0] = pinned_acquire();
+            pin[1] = pinned_acquire();
+            ok = pin[0] && pin[1];
+        }
+        int bsel = 0;
+        for (long long c = r; c < nchunks; c += R, bsel ^= 1) {
+            if (!ok) {
+                failed(c, "ingest reader: stream / pinned buffer setup failed");
+                continue;  // mark every chunk of this reader so the consumer never waits forever
             }
-            got += (size_t)r;
+            if (sh.abort.load()) {
+                failed(c, "");
+                continue;
+            }
+            const long long pos = b0 + c * chunk;
+            const size_t want = (size_t)std::min<long long>(chunk, b1 - pos);
+            if (last[bsel] >= 0) cudaEventSynchronize(events[(size_t)last[bsel]]);  // the buffer's previous copy has left it
+            if (src.host) {
+                memcpy(pin[bsel], src.host + pos, want);
+            } else {
+                size_t got = 0;
+                while (got < want) {
+                    const ssize_t n = pread(src.fd, pin[bsel] + got, want - got, (off_t)(pos + (long long)got));
+                    if (n <= 0) break;
+                    got += (size_t)n;
+                }
+                if (got < want) {
+                    failed(c, "short read at byte " + std::to_string(pos + (long long)got));
+                    continue;
+                }
+            }
+            cudaError_t e = cudaMemcpyAsync(d_dst + (pos - b0), pin[bsel], want, cudaMemcpyHostToDevice, rs);
+            if (e == cudaSuccess) e = cudaEventRecord(events[(size_t)c], rs);
+            if (e != cudaSuccess) {
+                failed(c, std::string("H2D copy: ") + cudaGetErrorString(e));
+                continue;
+            }
+            last[bsel] = c;
+            std::lock_guard<std::mutex> lk(sh.mu);
+            sh.state[(size_t)c] = 1;
+            sh.cv.notify_all();
         }
-        if (rc) break;
-        cudaError_t e = cudaMemcpyAsync(d_dst + (pos - b0), pin[s], want, cudaMemcpyHostToDevice, copy_st);
-        if (e == cudaSuccess) e = cudaEventRecord(done[s], copy_st);
-        if (e != cudaSuccess) rc = fail(APM_ECUDA, "H2D copy: %s", cudaGetErrorString(e));
-        used[s] = true;
-        pos += (long long)want;
-        if (!rc) rc = on_chunk(pos, done[s]);
+        if (rs) {
+            cudaStreamSynchronize(rs);  // the pinned buffers go back to the pool: nothing may still read them
+            cudaStreamDestroy(rs);
+        }
+        pinned_release(pin[0]);
+        pinned_release(pin[1]);
+    };
+    std::vector<std::thread> threads;
+    for (int r = 0; r < R; ++r) threads.emplace_back(reader, r);
+    int rc = APM_OK;
+    for (long long c = 0; c < nchunks && !rc; ++c) {
+        int stt;
+        {
+            std::unique_lock<std::mutex> lk(sh.mu);
+            sh.cv.wait(lk, [&] { return sh.state[(size_t)c] != 0; });
+            stt = sh.state[(size_t)c];
+        }
+        if (stt < 0) {
+            std::lock_guard<std::mutex> lk(sh.mu);
+            rc = fail(sh.err.rfind("short read", 0) == 0 ? APM_EIO : APM_ECUDA, "%s", sh.err.empty() ? "ingest aborted" : sh.err.c_str());
+            break;
+        }
+        if (cudaStreamWaitEvent(st, events[(size_t)c], 0) != cudaSuccess) rc = fail(APM_ECUDA, "cudaStreamWaitEvent failed");
+        if (!rc) rc = on_chunk(std::min(b1, b0 + (c + 1) * chunk));
     }
-    cudaStreamSynchronize(copy_st);
-    cudaEventDestroy(done[0]);
-    cudaEventDestroy(done[1]);
+    if (rc) sh.abort = true;
+    for (auto &t : threads) t.join();
+    for (auto &ev : events) cudaEventDestroy(ev);
     return rc;
 }
 
@@ -1632,25 +1753,31 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
         tl_err = keep;
         return code;
     };
-    for (int g = 0; g < G; ++g) {
+    const int readers = ingest_reader_count(opt, G);
+    // One host thread per GPU: plan construction, text ingest and kernel launches of the GPUs proceed side by side
+    // (with one thread the 8-GPU file run was one core's pread speed).  Errors are collected per job.
+    std::vector<int> job_rc(G, APM_OK);
+    std::vector<std::string> job_err(G);
+    auto run_job = [&](int g) -> int {
         DevJob &j = jobs[g];
+        int rc = APM_OK;
         j.dev = (restore + g) % ndev;  // the current device first
-        if (cudaSetDevice(j.dev) != cudaSuccess) return bail(fail(APM_ECUDA, "cudaSetDevice(%d) failed", j.dev));
+        if (cudaSetDevice(j.dev) != cudaSuccess) return fail(APM_ECUDA, "cudaSetDevice(%d) failed", j.dev);
         if (cudaStreamCreateWithFlags(&j.st, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&j.copy_st, cudaStreamNonBlocking) != cudaSuccess)
-            return bail(fail(APM_ECUDA, "cudaStreamCreate failed on device %d", g));
-        mark("stream create", nullptr);
-        if ((rc = apm_plan_create(patterns, pattern_len, nb_patterns, approx_factor, &j.plan))) return bail(rc);
-        mark("plan create", nullptr);
+            return fail(APM_ECUDA, "cudaStreamCreate failed on device %d", g);
+        if (g == 0) mark("stream create", nullptr);
+        if ((rc = apm_plan_create(patterns, pattern_len, nb_patterns, approx_factor, &j.plan))) return rc;
+        if (g == 0) mark("plan create", nullptr);
         if (hits && hits->max_hits > 0) {  // every GPU may find up to max_hits positions
             if (dev_alloc((void **)&j.d_hits, (hits->max_hits + 1) * sizeof(unsigned long long)) != cudaSuccess)
-                return bail(fail(APM_ENOMEM, "cudaMalloc of the hit buffer (%llu entries) failed", hits->max_hits));
+                return fail(APM_ENOMEM, "cudaMalloc of the hit buffer (%llu entries) failed", hits->max_hits);
             if (cudaMemsetAsync(j.d_hits, 0, sizeof(unsigned long long), j.st) != cudaSuccess)
-                return bail(fail(APM_ECUDA, "cudaMemsetAsync failed"));
-            if ((rc = apm_plan_set_hit_buffer(j.plan, j.d_hits + 1, hits->max_hits, j.d_hits))) return bail(rc);
+                return fail(APM_ECUDA, "cudaMemsetAsync failed");
+            if ((rc = apm_plan_set_hit_buffer(j.plan, j.d_hits + 1, hits->max_hits, j.d_hits))) return rc;
         }
         if (shard == SHARD_PATTERNS) {
-            if (G > 1 && (rc = apm_plan_set_pattern_shard(j.plan, g, G))) return bail(rc);
+            if (G > 1 && (rc = apm_plan_set_pattern_shard(j.plan, g, G))) return rc;
             j.j0 = 0;
             j.j1 = W;
         } else {  // database shard g owns window STARTS [j0, j1); bytes up to j1 + mmax - 1 (halo)
@@ -1667,44 +1794,61 @@ int count_impl(const TextSource &src, long long N, const char *const *patterns, 
         const long long seg_bytes = nseg == 1 ? j.b1 - j.b0 : seg_w + mmax - 1;
         if (dev_alloc((void **)&j.d_text, (size_t)std::max<long long>(16, seg_bytes)) != cudaSuccess ||
             (nseg > 1 && dev_alloc((void **)&j.d_text2, (size_t)std::max<long long>(16, seg_bytes)) != cudaSuccess))
-            return bail(fail(APM_ENOMEM, "cudaMalloc of %lld text bytes failed on device %d", seg_bytes, g));
-        mark("text malloc", nullptr);
+            return fail(APM_ENOMEM, "cudaMalloc of %lld text bytes failed on device %d", seg_bytes, g);
+        if (g == 0) mark("text malloc", nullptr);
+        // counting is launched for batches of complete windows while later chunks are still being read
+        const long long batch = opt.mode == MODE_DIRECT ? (long long)(8 << 20) : (long long)(64 << 20);
         for (long long sgi = 0; sgi < nseg; ++sgi) {
             const long long w0 = j.j0 + sgi * seg_w, w1 = std::min(j.j1, w0 + seg_w);
             const long long sb0 = w0, sb1 = std::min(N, w1 + mmax - 1);
             const int bi = (int)(sgi & 1);
             uint8_t *d_seg = bi ? j.d_text2 : j.d_text;
+            cudaEvent_t wait_before = nullptr;
             if (nseg > 1) {
                 if (!j.seg_done[bi]) {
                     if (cudaEventCreateWithFlags(&j.seg_done[bi], cudaEventDisableTiming) != cudaSuccess)
-                        return bail(fail(APM_ECUDA, "cudaEventCreate failed"));
-                } else if (cudaStreamWaitEvent(j.copy_st, j.seg_done[bi], 0) != cudaSuccess) {  // buffer still being counted
-                    return bail(fail(APM_ECUDA, "cudaStreamWaitEvent failed"));
+                        return fail(APM_ECUDA, "cudaEventCreate failed");
+                } else {
+                    wait_before = j.seg_done[bi];  // the buffer is still being counted
                 }
             }
-            // file source: the windows whose bytes (incl. the halo) have arrived are counted on j.st while the host
-            // is still reading the next 32 MiB chunk; only the tail of the segment waits for its last chunk
             long long counted_to = w0;
-            auto on_chunk = [&](long long bytes_end, cudaEvent_t ev) -> int {
+            auto on_chunk = [&](long long bytes_end) -> int {
                 const long long w_end = bytes_end >= sb1 ? w1 : std::min(w1, bytes_end - (mmax - 1));
-                if (w_end - counted_to < (bytes_end >= sb1 ? 1 : (long long)(8 << 20))) return APM_OK;  // batch small steps
-                if (cudaStreamWaitEvent(j.st, ev, 0) != cudaSuccess) return fail(APM_ECUDA, "cudaStreamWaitEvent failed");
+                if (w_end - counted_to < (bytes_end >= sb1 ? 1 : batch)) return APM_OK;  // batch small steps
                 const int r = apm_plan_count_device(j.plan, d_seg, (unsigned long long)sb0, (unsigned long long)(sb1 - sb0),
                                                     (unsigned long long)N, (unsigned long long)counted_to,
                                                     (unsigned long long)w_end, j.st);
                 counted_to = w_end;
                 return r;
             };
-            if ((rc = copy_range_to_device(src, sb0, sb1, d_seg, j.st, j.copy_st, on_chunk))) return bail(rc);
-            if (sgi == 0) mark("text H2D", src.host ? j.st : nullptr);
+            if ((rc = copy_range_to_device(src, sb0, sb1, d_seg, j.st, j.copy_st, wait_before, readers, on_chunk))) return rc;
+            if (sgi == 0 && g == 0) mark("text H2D", src.host ? j.st : nullptr);
             if (counted_to < w1 &&
                 (rc = apm_plan_count_device(j.plan, d_seg, (unsigned long long)sb0, (unsigned long long)(sb1 - sb0),
                                             (unsigned long long)N, (unsigned long long)counted_to, (unsigned long long)w1, j.st)))
-                return bail(rc);
-            if (nseg > 1 && cudaEventRecord(j.seg_done[bi], j.st) != cudaSuccess)
-                return bail(fail(APM_ECUDA, "cudaEventRecord failed"));
+                return rc;
+            if (nseg > 1 && cudaEventRecord(j.seg_done[bi], j.st) != cudaSuccess) return fail(APM_ECUDA, "cudaEventRecord failed");
         }
-        mark("count kernels", j.st);
+        if (g == 0) mark("count kernels", j.st);
+        return APM_OK;
+    };
+    if (G == 1) {
+        if ((rc = run_job(0))) return bail(rc);
+    } else {
+        std::vector<std::thread> workers;
+        for (int g = 0; g < G; ++g)
+            workers.emplace_back([&, g] {
+                job_rc[g] = run_job(g);
+                if (job_rc[g]) job_err[g] = tl_err;  // tl_err is per thread
+            });
+        for (auto &t : workers) t.join();
+        for (int g = 0; g < G; ++g)
+            if (job_rc[g]) {
+                tl_err = job_err[g];
+                return bail(job_rc[g]);
+            }
+        cudaSetDevice(restore);
     }
     // ---- combine the per-GPU count vectors
     bool reduced_on_device = false;
