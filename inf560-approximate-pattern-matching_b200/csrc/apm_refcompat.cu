@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/apm_b200.h"
@@ -39,18 +40,108 @@ void report(const char *where) { fprintf(stderr, "apm_refcompat: %s: %s\n", wher
 // ---- invoke_kernel / write_kernel_result -----------------------------------------------------------
 struct PorJob {
     apm_plan *plan = nullptr;
-    unsigned char *d_text = nullptr;
+    unsigned char *d_text = nullptr;  // private copy of the text, or nullptr when the cached copy is used
+    bool uses_cache = false;
     cudaStream_t st = nullptr;
     int initial = 0;
 };
+
+// The reference's worker calls invoke_kernel once per pattern with the SAME broadcast text
+// (patterns_over_ranks.c:323) and its kernel wrapper re-uploads the whole buffer every time
+// (patterns_over_ranks.cu:79-91): P x the PCIe traffic.  Here the device copy is kept between calls and reused
+// when the next call passes the same (device, buf, n_bytes) and the buffer's fingerprint (both ends + 256 strided
+// samples) is unchanged.  APM_REFCOMPAT_TEXT_CACHE=0 switches the cache off (every call uploads).
+struct TextCache {
+    std::mutex mu;
+    int dev = -1;
+    const char *buf = nullptr;
+    int n_bytes = 0;
+    unsigned long long fp = 0;
+    unsigned char *d_text = nullptr;
+    cudaEvent_t ready = nullptr;  // recorded behind the upload
+    int refs = 0;                 // jobs in flight that read d_text
+};
+TextCache g_text;
+
+unsigned long long text_fingerprint(const char *buf, int n) {
+    unsigned long long h = 1469598103934665603ull ^ (unsigned long long)n;
+    auto mix = [&](const char *p, int len) {
+        for (int i = 0; i < len; ++i) h = (h ^ (unsigned char)p[i]) * 1099511628211ull;
+    };
+    const int edge = n < 4096 ? n : 4096;
+    mix(buf, edge);
+    mix(buf + n - edge, edge);
+    if (n > 2 * 4096)
+        for (int s = 0; s < 256; ++s) {
+            const long long off = (long long)(n - 64) * s / 256;
+            mix(buf + off, 64);
+        }
+    return h;
+}
+
+bool text_cache_enabled() {
+    static const bool on = !(getenv("APM_REFCOMPAT_TEXT_CACHE") && atoi(getenv("APM_REFCOMPAT_TEXT_CACHE")) == 0);
+    return on;
+}
 
 void por_release(PorJob *j) {
     if (!j) return;
     if (j->st) cudaStreamSynchronize(j->st);
     if (j->plan) apm_plan_destroy(j->plan);
     if (j->d_text) cudaFree(j->d_text);
+    if (j->uses_cache) {
+        std::lock_guard<std::mutex> lk(g_text.mu);
+        g_text.refs--;
+    }
     if (j->st) cudaStreamDestroy(j->st);
     delete j;
+}
+
+// device copy of buf[0, n_bytes) for job j, uploaded on j->st or shared with the previous calls; nullptr on failure
+const unsigned char *por_text(PorJob *j, const char *buf, int n_bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (text_cache_enabled()) {
+        const unsigned long long fp = text_fingerprint(buf, n_bytes);
+        std::lock_guard<std::mutex> lk(g_text.mu);
+        if (g_text.d_text && g_text.dev == dev && g_text.buf == buf && g_text.n_bytes == n_bytes && g_text.fp == fp) {
+            if (cudaStreamWaitEvent(j->st, g_text.ready, 0) != cudaSuccess) return nullptr;
+            g_text.refs++;
+            j->uses_cache = true;
+            return g_text.d_text;
+        }
+        if (g_text.refs == 0) {  // replace the cached text (nobody reads the old one any more)
+            if (g_text.d_text) {
+                cudaSetDevice(g_text.dev);
+                cudaFree(g_text.d_text);
+                cudaSetDevice(dev);
+                g_text.d_text = nullptr;
+            }
+            if (!g_text.ready && cudaEventCreateWithFlags(&g_text.ready, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            if (cudaMalloc((void **)&g_text.d_text, (size_t)n_bytes) != cudaSuccess) {
+                g_text.d_text = nullptr;
+                return nullptr;
+            }
+            if (cudaMemcpyAsync(g_text.d_text, buf, (size_t)n_bytes, cudaMemcpyHostToDevice, j->st) != cudaSuccess ||
+                cudaEventRecord(g_text.ready, j->st) != cudaSuccess) {
+                cudaFree(g_text.d_text);
+                g_text.d_text = nullptr;
+                return nullptr;
+            }
+            g_text.dev = dev;
+            g_text.buf = buf;
+            g_text.n_bytes = n_bytes;
+            g_text.fp = fp;
+            g_text.refs = 1;
+            j->uses_cache = true;
+            return g_text.d_text;
+        }
+    }
+    // private copy: cache off, or another text is still being searched
+    if (cudaMalloc((void **)&j->d_text, (size_t)n_bytes) != cudaSuccess ||
+        cudaMemcpyAsync(j->d_text, buf, (size_t)n_bytes, cudaMemcpyHostToDevice, j->st) != cudaSuccess)
+        return nullptr;
+    return j->d_text;
 }
 
 // ---- initializeGPU / getGPUResult --------------------------------------------------------------------
@@ -144,14 +235,13 @@ int *invoke_kernel(char *buf, int n_bytes, char *my_pattern, int pattern_length,
         return NULL;
     }
     if (n_bytes > 0) {
-        if (cudaStreamCreateWithFlags(&j->st, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaMalloc((void **)&j->d_text, (size_t)n_bytes) != cudaSuccess ||
-            cudaMemcpyAsync(j->d_text, buf, (size_t)n_bytes, cudaMemcpyHostToDevice, j->st) != cudaSuccess) {
+        const unsigned char *d_text = nullptr;
+        if (cudaStreamCreateWithFlags(&j->st, cudaStreamNonBlocking) != cudaSuccess || !(d_text = por_text(j, buf, n_bytes))) {
             fprintf(stderr, "apm_refcompat: invoke_kernel: %s\n", cudaGetErrorString(cudaGetLastError()));
             por_release(j);
             return NULL;
         }
-        if (apm_plan_count_device(j->plan, j->d_text, 0, (unsigned long long)n_bytes, (unsigned long long)n_bytes, 0,
+        if (apm_plan_count_device(j->plan, d_text, 0, (unsigned long long)n_bytes, (unsigned long long)n_bytes, 0,
                                   (unsigned long long)n_bytes, j->st) != APM_OK) {
             report("invoke_kernel");
             por_release(j);

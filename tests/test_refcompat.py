@@ -116,3 +116,43 @@ def test_approach_entry_points_print_the_reference_lines(which, tmp_path):
     banner = "Approximate Pattern Matching:" if which == "patterns" else "Approximate Pattern Mathing:"
     assert lines[0].startswith(banner)
     assert len(counts) == len(case["patterns"])  # rank 1 printed nothing
+
+
+@pytest.mark.gpu
+def test_invoke_kernel_text_cache_reuse_and_invalidation():
+    """patterns_over_ranks.c:323 calls invoke_kernel once per pattern with the same broadcast text: the device copy is
+    reused; new content at the same address (or another length) is noticed; several jobs may be in flight."""
+    import ctypes as C
+    L = refcompat.lib()
+    n, k = 80_000, 2
+    text = oracle.synth_text(0x5EED0001, 9, n).tobytes()
+    pats = [text[1000:1032], text[40_000:40_050], text[79_000:79_064], b"ACGTTGCAACGTTGCAACGT"]
+    want = oracle.count_matches(text, pats, k)
+    tb = C.create_string_buffer(text, n)
+
+    def invoke(buf, nbytes, p, local):
+        pb = C.create_string_buffer(p, len(p))
+        return L.invoke_kernel(C.addressof(buf), nbytes, C.addressof(pb), len(p), k, C.byref(local))
+
+    # all four jobs in flight on the same text, results fetched afterwards (as an OpenMP team of callers would)
+    locals_ = [C.c_int(3) for _ in pats]
+    handles = [invoke(tb, n, p, loc) for p, loc in zip(pats, locals_)]
+    for h, loc in zip(handles, locals_):
+        L.write_kernel_result(C.byref(loc), h)
+    assert [loc.value - 3 for loc in locals_] == want
+    # same address, same length, different content in the middle and at the end
+    text2 = bytearray(text)
+    text2[40_000:40_050] = b"T" * 50
+    text2[-64:] = b"A" * 64
+    C.memmove(tb, bytes(text2), n)
+    want2 = oracle.count_matches(bytes(text2), pats, k)
+    got2 = []
+    for p in pats:
+        loc = C.c_int(0)
+        L.write_kernel_result(C.byref(loc), invoke(tb, n, p, loc))
+        got2.append(loc.value)
+    assert got2 == want2 and want2 != want
+    # a prefix of the same buffer
+    loc = C.c_int(0)
+    L.write_kernel_result(C.byref(loc), invoke(tb, 50_000, pats[0], loc))
+    assert loc.value == oracle.count_matches(bytes(text2[:50_000]), [pats[0]], k)[0]
