@@ -70,28 +70,36 @@ int apm_find_matches(const unsigned char *text, size_t n_bytes, const char *cons
                      unsigned long long max_hits, int *hit_pattern, unsigned long long *hit_start,
                      unsigned long long *n_hits);
 
-/* Options (process-wide, read when a call starts):
+/* Options (process-wide; a plan and a one-shot call take a snapshot when they start):
  *   "gpus"    = "1".."8" | "all"      devices used by the one-shot API (default 1)
  *   "shard"   = "db" | "patterns" | "auto"   how work is split over several GPUs (default auto)
  *   "kernel"  = "auto" | "sliced" | "myers" | "dp"
  *                 auto (default): window-sliced bit-parallel kernel (m <= 1024, <= 8 pattern symbols),
  *                 row-parallel Hyyro/Myers kernel otherwise (m <= 256), explicit DP for the rest;
- *                 every mode routes the truncated tail windows to the explicit-DP kernel;
  *                 dp: explicit-DP kernel for everything (in-GPU cross-check)
+ *   "tail"    = "auto" | "bitpar" | "dp"   truncated tail windows (sequential.c:131-136) of the bit-parallel patterns:
+ *                 bitpar (= auto): Hyyro/Myers bit-vector kernels, one thread (m <= 256) or one warp (m <= 1024) per
+ *                 window; dp: the explicit-DP kernel (its banded variant in band / filter mode)
  *   "mode"    = "direct" | "band" | "filter"
  *                 direct (default): every DP cell of every window is evaluated;
  *                 band: exact Ukkonen band |i-j| <= k (same counts, ~(2k+1)/m of the work);
- *                 filter: exact pigeonhole filter -- one rolling-hash scan of the text against the seeds of all
- *                 patterns (k+1 pieces each), banded verification of the candidate windows only; patterns whose
- *                 pieces are shorter than 8 symbols (or k > 16) and rounds whose candidates overflow the buffer
- *                 go through the band kernel.  Same counts; work ~ text bytes instead of text bytes x patterns.
- *   "filter_cand_mb" = candidate buffer of filter mode in MiB (default 128)
+ *                 filter: exact pigeonhole filter -- ONE scan of the text against the seeds of all patterns (k+1
+ *                 pieces each), verification of the seed hits only; patterns whose pieces are shorter than 8
+ *                 symbols (or k > 16) and rounds whose candidates overflow the buffer go through the band kernel.
+ *                 Same counts; work ~ text bytes instead of text bytes x patterns.
+ *   "filter_scan" = "auto" | "dna" | "hash"   scan of filter mode: dna = 2-bit q-gram scan on a strided probe grid
+ *                 + seed-hit verification (pattern symbols all in ACGT, k <= 15; any text bytes); hash = rolling-hash
+ *                 scan + per-shift banded verification (any alphabet); auto (default) = dna when the patterns allow
+ *   "filter_cand_mb" = candidate buffers of filter mode in MiB (default 128)
+ *   "ingest_threads" = "auto" | 1..64   reader threads PER GPU of the chunked ingest (files and large pageable host
+ *                 buffers: pread / memcpy into pinned staging buffers, async H2D, counting overlapped); auto =
+ *                 host threads / GPUs, at most 8
  *   "cell"    = "auto" | "lop3" | "fma3" | "fma"   code of one DP cell in the window-sliced / band kernels:
  *                 lop3: 5 LOP3 (ALU pipe only); fma3: 4 LOP3 + 3 IMAD; fma: 4 LOP3 + 2 IMAD (FMA pipe takes the
  *                 subtractions); auto (default) picks per pattern-length class.  Same results, different speed.
  *   "reduce"  = "auto" | "p2p" | "nccl" | "host"   how the per-GPU count vectors of the one-shot API are combined
- *                 when "gpus" > 1: p2p = every GPU adds its vector into GPU 0's with system-scope atomics on NVLink
- *                 peer memory (our own kernel, no communicator); nccl = one in-place ncclAllReduce per device (NCCL
+ *                 when "gpus" > 1: p2p = GPU 0 pulls every other GPU's vector through NVLink peer memory and adds it to
+ *                 its own (our own kernel, stream ordered, no communicator, no cross-device atomics); nccl = one in-place ncclAllReduce per device (NCCL
  *                 loaded at run time); host = host-side sum; auto (default) = p2p, else nccl, else host
  *   "text_chunk_mb" = one-shot API: a GPU's shard with more than this many Mi window starts (default 32768) is
  *                 streamed through two device buffers, segment by segment with its own halo, so the device memory

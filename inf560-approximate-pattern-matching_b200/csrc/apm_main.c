@@ -6,7 +6,8 @@
  *
  * The optional trailing flag mirrors src/main.c:66-85 and selects how work is split over GPUs.
  * Extra knobs come from the environment so argv stays drop-in: APM_GPUS, APM_SHARD, APM_KERNEL, APM_MODE
- * (direct | band | filter -- all exact, same counts; the CLI defaults to filter), APM_CELL, APM_RBLOCK, APM_TILE; APM_INFO=1 adds the
+ * (direct | band | filter -- all exact, same counts; the CLI defaults to filter), APM_CELL, APM_RBLOCK, APM_TILE,
+ * APM_FILTER_SCAN, APM_INGEST_THREADS, APM_TAIL, APM_REDUCE (see include/apm_b200.h); APM_INFO=1 adds the
  * "(Rank 0) - TOTAL TIME ..." line of the parallel binary (patterns_over_ranks.c:223-226); APM_POSITIONS=n
  * additionally lists the first n matches as "Match of pattern <p> at byte j" (not in the reference);
  * APM_PATTERN_FILE=path appends one pattern per line of that file to the patterns of argv (argv is limited to
@@ -83,7 +84,9 @@ int main(int argc, char **argv) {
     apm_set_option("mode", "filter");
     if (set_from_env("APM_GPUS", "gpus") || set_from_env("APM_SHARD", "shard") ||
         set_from_env("APM_KERNEL", "kernel") || set_from_env("APM_RBLOCK", "rblock") ||
-        set_from_env("APM_TILE", "tile") || set_from_env("APM_MODE", "mode") || set_from_env("APM_CELL", "cell"))
+        set_from_env("APM_TILE", "tile") || set_from_env("APM_MODE", "mode") || set_from_env("APM_CELL", "cell") ||
+        set_from_env("APM_FILTER_SCAN", "filter_scan") || set_from_env("APM_INGEST_THREADS", "ingest_threads") ||
+        set_from_env("APM_TAIL", "tail") || set_from_env("APM_REDUCE", "reduce"))
         return 1;
 
     /* main.c:66-85: an explicit approach as last argument is consumed, not searched for */
