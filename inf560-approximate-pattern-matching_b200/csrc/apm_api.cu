@@ -285,6 +285,7 @@ struct Bucket {
 // patterns handled by the window-sliced kernel: one list for m <= 32 (MC = 32) and one for longer ones
 struct SlicedList {
     int MC = 64, npat = 0, mmin = 0, mmax = 0, mcp = 0;
+    int ragged = 0;  // 0: generic kernel; 1: single-block patterns with m % MC != 0 (compile-time block widths)
     std::vector<uint8_t> codes;  // [npat][mcp]
     std::vector<int> m, id;
     uint8_t *d_codes = nullptr;
@@ -408,13 +409,20 @@ int auto_rblock(int NW) { return NW <= 2 ? 4 : (NW <= 4 ? 2 : 1); }
 // bit-parallel patterns `ids`, uploaded to the device.
 int build_lists(apm_plan *pl, const std::vector<int> &ids_in, std::vector<Bucket> &buckets, std::vector<SlicedList> &sliced) {
     std::vector<std::vector<int>> by_nw(kMaxWords + 1);
-    std::vector<int> sliced_ids[2];
+    // window-sliced lists: by register-block width (MC = 32 for m <= 32, else 64) and -- in direct mode with the
+    // automatic cell choice -- by raggedness, so that lengths that are not a multiple of MC run on the kernels with
+    // compile-time block widths (RG = 1 / 2) while multiples of MC stay on the generic kernel
+    const bool split = pl->opt.mode == MODE_DIRECT && pl->opt.cell < 0;
+    std::vector<int> sliced_ids[5];  // {MC 32 full, MC 32 ragged, MC 64 full (m = 64), MC 64 ragged (33..63), m > 64}
     for (int p : ids_in) {
         const int m = (int)pl->pats[p].size();
         const bool sliced_ok = m <= kSlicedMaxLen && pl->nplanes <= kSlicedMaxPlanes &&
                                (pl->opt.kernel == KERNEL_SLICED || pl->opt.kernel == KERNEL_AUTO);
-        if (sliced_ok) sliced_ids[m <= 32 ? 0 : 1].push_back(p);
-        else by_nw[(m + 31) / 32].push_back(p);
+        if (!sliced_ok) by_nw[(m + 31) / 32].push_back(p);
+        else if (!split) sliced_ids[m <= 32 ? 0 : 2].push_back(p);
+        else if (m <= 32) sliced_ids[m == 32 ? 0 : 1].push_back(p);
+        else if (m <= 64) sliced_ids[m == 64 ? 2 : 3].push_back(p);
+        else sliced_ids[4].push_back(p);
     }
     for (int NW = 1; NW <= kMaxWords; ++NW) {
         auto &ids = by_nw[NW];
@@ -455,13 +463,14 @@ int build_lists(apm_plan *pl, const std::vector<int> &ids_in, std::vector<Bucket
         if ((rc = upload(&b.d_group_pat, b.group_pat))) return rc;
         buckets.push_back(std::move(b));
     }
-    for (int which = 0; which < 2; ++which) {
+    for (int which = 0; which < 5; ++which) {
         auto &ids = sliced_ids[which];
         if (ids.empty()) continue;
         std::stable_sort(ids.begin(), ids.end(),
                          [&](int a, int b) { return pl->pats[a].size() < pl->pats[b].size(); });
         SlicedList l;
-        l.MC = which == 0 ? 32 : 64;
+        l.MC = which <= 1 ? 32 : 64;
+        l.ragged = split && (which == 1 || which == 3) ? 1 : 0;
         l.npat = (int)ids.size();
         l.mmin = (int)pl->pats[ids.front()].size();
         l.mmax = (int)pl->pats[ids.back()].size();
@@ -697,9 +706,9 @@ int launch_myers(apm_plan *pl, Bucket &b, const uint8_t *d_buf, long long buf_le
     return APM_OK;
 }
 
-template <int MC, int CELL>
+template <int MC, int CELL, int RG = 0>
 int launch_sliced_mc(apm_plan *pl, SlicedList &l, SlicedArgs a, long long nwin, cudaStream_t st) {
-    auto fn = sliced_count_kernel<MC, CELL>;
+    auto fn = sliced_count_kernel<MC, CELL, RG>;
     const long long ntiles = (nwin + kSlicedTile - 1) / kSlicedTile;
     const int rowsU = sliced_rowsU(l.mmax);
     const size_t smem = sliced_smem_bytes(pl->nplanes, rowsU);
@@ -833,6 +842,8 @@ int launch_sliced(apm_plan *pl, SlicedList &l, const uint8_t *d_buf, long long b
     // pattern is one register block (m <= 32: 4 LOP3 + 2 IMAD, m <= 64: 4 LOP3 + 3 IMAD); register-file operand
     // bandwidth, not the pipes, limits the co-issue (tools/ubench/pipe_mix.cu), so the gain is ~6 %
     const int cell = pl->opt.cell >= 0 ? pl->opt.cell : (l.MC == 32 ? 2 : (l.mmax <= 64 ? 1 : 0));
+    // lengths that are not a multiple of the block width: kernels with compile-time block widths (apm_sliced.cuh)
+    if (l.ragged == 1) return l.MC == 32 ? launch_sliced_mc<32, 2, 1>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 1, 1>(pl, l, a, lim - w0, st);
     if (cell == 2)
         return l.MC == 32 ? launch_sliced_mc<32, 2>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 2>(pl, l, a, lim - w0, st);
     if (cell == 1)

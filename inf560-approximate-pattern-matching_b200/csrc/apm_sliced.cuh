@@ -277,6 +277,74 @@ __device__ __forceinline__ void sliced_sweep(const unsigned char *__restrict__ u
     }
 }
 
+// The same pipelined sweep for a block of which only the first W columns are computed (W a compile-time multiple
+// of 4, W <= MC): the ragged last (or only) column block of patterns whose length is not a multiple of MC.  The
+// columns [width, W) are evaluated (they are real DP columns) and then put back to the neutral value, the columns
+// [W, MC) are never touched.  The run-time-width sweep above (FULL = false) cannot be software pipelined and loses
+// 9-19 % on such lengths; with W known at compile time the ragged block runs like a full one.
+template <int MC, int CELL, int W, bool VIN, bool VOUT>
+__device__ __forceinline__ void sliced_sweep_w(const unsigned char *__restrict__ urow, const uint8_t *__restrict__ pc,
+                                               int rows, int width, uint32_t plane_bytes, uint32_t (&hp)[MC],
+                                               uint32_t (&hm)[MC], uint2 *__restrict__ vs, long long vstride,
+                                               uint32_t neg1) {
+    static_assert(W % 4 == 0 && W >= 4 && W <= MC, "W must be a multiple of 4 in [4, MC]");
+    constexpr int G = 8;                    // columns per pipeline group (the last group may hold 4)
+    constexpr int NG = (W + G - 1) / G;
+    constexpr int G0 = W < G ? W : G;       // size of the first group of a row
+    uint32_t code_next = __ldg(pc + 1);
+    uint2 vin = make_uint2(0xFFFFFFFFu, 0u);
+    if constexpr (VIN) vin = vs[0];
+    const unsigned char *e = urow + (uint32_t)__ldg(pc) * plane_bytes;
+    uint2 buf[G / 2];
+#pragma unroll
+    for (int q = 0; q < G0 / 2; ++q) buf[q] = *reinterpret_cast<const uint2 *>(e + q * 8);
+#pragma unroll 1
+    for (int i = 0; i < rows; ++i) {
+        const unsigned char *e_next = urow + code_next * plane_bytes;
+        code_next = __ldg(pc + i + 2);
+        uint32_t ap = vin.x, am = vin.y;
+        if constexpr (VIN) vin = vs[(long long)(i + 1) * vstride];
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) {
+            const int gs = (W - gi * G) < G ? (W - gi * G) : G;  // compile-time after unrolling
+            uint2 cur[G / 2];
+#pragma unroll
+            for (int q = 0; q < G / 2; ++q) cur[q] = buf[q];
+            const int c1 = (gi + 1) * G;
+            if (gi + 1 < NG) {
+                const int ngs = (W - c1) < G ? (W - c1) : G;
+#pragma unroll
+                for (int q = 0; q < G / 2; ++q)
+                    if (q < ngs / 2) buf[q] = *reinterpret_cast<const uint2 *>(e + ((c1 + 2 * q) >> 5) * kURowBytes + ((c1 + 2 * q) & 31) * 4);
+            } else {
+#pragma unroll
+                for (int q = 0; q < G0 / 2; ++q) buf[q] = *reinterpret_cast<const uint2 *>(e_next + q * 8);
+            }
+#pragma unroll
+            for (int cc = 0; cc < G; ++cc)
+                if (cc < gs) sliced_cell<CELL>((cc & 1) ? cur[cc >> 1].y : cur[cc >> 1].x, ap, am, hp[gi * G + cc], hm[gi * G + cc], neg1);
+        }
+        if constexpr (VOUT) vs[(long long)i * vstride] = make_uint2(ap, am);
+        e = e_next;
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j)  // columns >= width: back to the neutral boundary value (they add a constant)
+        if (j >= width) { hp[j] = 0xFFFFFFFFu; hm[j] = cell_plus_second_plane<CELL>(); }
+}
+
+// run-time dispatch over the instantiated widths: W = width rounded up to a multiple of STEP
+template <int MC, int CELL, int STEP, bool VIN, int W = STEP>
+__device__ __forceinline__ void sliced_sweep_dispatch(int wr, const unsigned char *__restrict__ urow, const uint8_t *__restrict__ pc,
+                                                      int rows, int width, uint32_t plane_bytes, uint32_t (&hp)[MC],
+                                                      uint32_t (&hm)[MC], uint2 *__restrict__ vs, long long vstride, uint32_t neg1) {
+    if constexpr (W >= MC) {
+        sliced_sweep_w<MC, CELL, MC, VIN, false>(urow, pc, rows, width, plane_bytes, hp, hm, vs, vstride, neg1);
+    } else {
+        if (wr <= W) sliced_sweep_w<MC, CELL, W, VIN, false>(urow, pc, rows, width, plane_bytes, hp, hm, vs, vstride, neg1);
+        else sliced_sweep_dispatch<MC, CELL, STEP, VIN, W + STEP>(wr, urow, pc, rows, width, plane_bytes, hp, hm, vs, vstride, neg1);
+    }
+}
+
 // tot += acc (bit-sliced): acc has NA planes, tot kSlicedTotPlanes
 template <int NA>
 __device__ __forceinline__ void planes_add(uint32_t (&tot)[kSlicedTotPlanes], const uint32_t (&acc)[NA]) {
@@ -349,7 +417,15 @@ __device__ __forceinline__ TileGeom sliced_stage_tile(const SlicedArgs &a, long 
 // (uniform addresses, L1 broadcast).  MC = columns per register block: 32 (patterns m <= 32, one block)
 // or 64 (any m <= kSlicedMaxLen, ceil(m/64) blocks chained through the global boundary scratch).
 // ------------------------------------------------------------------------------------------------
-template <int MC, int CELL>
+// RG = 0: any pattern lengths, ragged blocks through the run-time-width sweep (the round-1 kernel, unchanged).
+// RG = 1: single-block patterns (m <= MC) swept with the compile-time width m rounded up to a multiple of 4
+//         (m = 50: 93.8 -> 103.3 TCUPS, m = 20: 76.6 -> 99.2; profiles/r02_len_sweep.txt).
+// The host keeps lengths that are multiples of MC, and all multi-block patterns, on RG = 0 (its register allocation
+// is what the headline number was tuned on) and routes single-block ragged lengths to RG = 1 when the cell code is
+// chosen automatically.  (A variant with compile-time widths for the LAST block of multi-block patterns was built
+// and measured 3-10 % SLOWER than the run-time-width sweep for every m > 64 -- the extra sweep instantiations cost
+// the multi-block kernel its register allocation -- and was dropped.)
+template <int MC, int CELL, int RG = 0>
 __global__ void __launch_bounds__(kSlicedThreads, MC == 64 ? 3 : 4) sliced_count_kernel(const SlicedArgs a) {
     static_assert(MC == 32 || MC == 64, "MC must be 32 or 64");
     if (a.run_if && *a.run_if == 0u) return;
@@ -416,7 +492,9 @@ __global__ void __launch_bounds__(kSlicedThreads, MC == 64 ? 3 : 4) sliced_count
                     uint32_t hp[MC], hm[MC];
 #pragma unroll
                     for (int j = 0; j < MC; ++j) { hp[j] = 0xFFFFFFFFu; hm[j] = cell_plus_second_plane<CELL>(); }  // D[0][j] - D[0][j-1] = +1
-                    if (MC == 32 || nblk == 1) {
+                    if constexpr (RG == 1) {
+                        sliced_sweep_dispatch<MC, CELL, 4, false, (MC == 64 ? 36 : 4)>((width + 3) & ~3, ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
+                    } else if (MC == 32 || nblk == 1) {
                         if (width == MC) sliced_sweep<MC, CELL, true, false, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
                         else sliced_sweep<MC, CELL, false, false, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
                     } else if (b == 0) {
