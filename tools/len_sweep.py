@@ -12,7 +12,8 @@ n = 64 << 20
 text = torch.empty(n, dtype=torch.uint8, device="cuda")
 apm_b200.synth_text_device(text.data_ptr(), TEXT_SEED, 0, n); torch.cuda.synchronize()
 st = torch.cuda.current_stream().cuda_stream
-for m in (12, 20, 24, 28, 31, 32, 36, 40, 48, 50, 52, 56, 60, 63, 64, 65, 72, 96, 100, 128, 136, 192, 200, 256, 500, 1000):
+LENS = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else None
+for m in LENS or (12, 20, 24, 28, 31, 32, 36, 40, 48, 50, 52, 56, 60, 63, 64, 65, 72, 96, 100, 128, 136, 192, 200, 256, 500, 1000):
     P = 256 if m <= 64 else 64; slab = max(1 << 18, (8 << 20) * 64 * 64 // (m * m) * 64 // P)
     slab = min(slab, n - 2000 - m)
     pats, _, _ = make_patterns(TEXT_SEED, n, P, m, 7)

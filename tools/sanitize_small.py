@@ -29,6 +29,18 @@ for cell in ("lop3", "fma3", "fma"):
     ok &= got == want
     print("cell", cell, "ok" if got == want else f"MISMATCH {got} {want}")
 apm_b200.set_option("cell", "auto")
+# round 2: both filter scans, both tail kernels, ragged single-block lengths, k up to 15
+pats2 = [text[200:212], text[500:520], text[700:750], text[1000:1063], text[5000:5200], text[-31:] + b"ACGTACGTACGTA"]
+for k2 in (0, 1, 5):
+    want2 = oracle.count_matches(text, pats2, k2)
+    for mode, scan, tail in (("direct", "auto", "bitpar"), ("direct", "auto", "dp"), ("filter", "dna", "bitpar"),
+                             ("filter", "hash", "dp"), ("band", "auto", "bitpar")):
+        apm_b200.set_option("mode", mode); apm_b200.set_option("filter_scan", "auto" if k2 == 0 and scan == "dna" else scan)
+        apm_b200.set_option("tail", tail)
+        got = apm_b200.count_matches(text, pats2, k2)
+        ok &= got == want2
+        print("round2", k2, mode, scan, tail, "ok" if got == want2 else f"MISMATCH {got} {want2}")
+apm_b200.set_option("filter_scan", "auto"); apm_b200.set_option("tail", "auto"); apm_b200.set_option("mode", "direct")
 for mode in ("direct", "band", "filter"):
     apm_b200.set_option("mode", mode)
     counts, hits, n_hits = apm_b200.find_matches(text, pats, 3, max_hits=64)
