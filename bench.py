@@ -525,7 +525,7 @@ def run_ours(args) -> None:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             captures = json.load(f)
         for name, tr in captures.items():
-            if (name.startswith("sliced_count_kernel<64, 1>") and args.kernel in ("auto", "sliced")
+            if (name.startswith("sliced_count_kernel<64, 3>") and args.kernel in ("auto", "sliced")
                     and tr.get("slab_windows") == slab and tr.get("patterns") == NB_PATTERNS):
                 traffic = tr["dram_bytes_per_launch"]
     except Exception:
@@ -545,7 +545,7 @@ def run_ours(args) -> None:
         "traffic": traffic, "traffic_source": "static: profiles/traffic.json, ncu --set full capture of this configuration "
         "(dram__bytes_read.sum + dram__bytes_write.sum per launch); null when this slab size was not captured",
         "algorithmic_bytes": algorithmic_bytes,
-        "kernel": "sliced_count_kernel<64, 1>" if args.kernel in ("auto", "sliced") else "myers_count_kernel<2,4,0>",
+        "kernel": "sliced_count_kernel<64, 3>" if args.kernel in ("auto", "sliced") else "myers_count_kernel<2,4,0>",
         "algorithmic_ops_per_unit": "10*m*ceil(m/32) = 1280 int32 ops per (pattern, window), SURVEY.md 8d",
         "peak_source": "measured in this run: max(LOP3+IADD3, LOP3+IMAD) dependency-free microbenchmark",
         "lop3_only_peak": peak1 / 1e12,

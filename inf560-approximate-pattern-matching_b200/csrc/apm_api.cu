@@ -71,7 +71,8 @@ struct Options {
     int rblock = 0;  // 0 = auto
     int tile = 0;    // 0 = auto
     int variant = 0; // column-step code variant (see myers_step_fma)
-    int cell = -1;   // DP-cell code of the sliced/band kernels: -1 auto, 0 = 5 LOP3, 1 = 4 LOP3 + 3 IMAD, 2 = 4 LOP3 + 2 IMAD
+    int cell = -1;   // DP-cell code of the sliced/band kernels: -1 auto, 0 = 5 LOP3, 1 = 4 LOP3 + 3 IMAD, 2 = 4 LOP3 + 2 IMAD,
+                     // 3 = 4 LOP3 + 3 IMAD ordered for the operand reuse cache (apm_sliced.cuh)
     int filter_scan = 0;  // mode=filter: 0 auto (2-bit DNA scan when the patterns allow it), 1 hashed scan, 2 DNA scan
     int tail = 0;    // truncated tail windows: 0 = bit-parallel kernels (apm_tail.cuh), 1 = explicit DP (apm_dp.cuh)
     int reduce = 0;  // multi-GPU count reduction: 0 auto (p2p kernel, else NCCL, else host), 1 nccl, 2 host sum, 3 p2p
@@ -413,7 +414,8 @@ int build_lists(apm_plan *pl, const std::vector<int> &ids_in, std::vector<Bucket
     // automatic cell choice -- by raggedness, so that lengths that are not a multiple of MC run on the kernels with
     // compile-time block widths (RG = 1 / 2) while multiples of MC stay on the generic kernel
     const bool split = pl->opt.mode == MODE_DIRECT && pl->opt.cell < 0;
-    std::vector<int> sliced_ids[5];  // {MC 32 full, MC 32 ragged, MC 64 full (m = 64), MC 64 ragged (33..63), m > 64}
+    // {MC 32 full, MC 32 ragged, MC 64 full (m = 64), MC 64 ragged (33..63), 65..224 (three CTAs per SM), longer}
+    std::vector<int> sliced_ids[6];
     for (int p : ids_in) {
         const int m = (int)pl->pats[p].size();
         const bool sliced_ok = m <= kSlicedMaxLen && pl->nplanes <= kSlicedMaxPlanes &&
@@ -422,7 +424,7 @@ int build_lists(apm_plan *pl, const std::vector<int> &ids_in, std::vector<Bucket
         else if (!split) sliced_ids[m <= 32 ? 0 : 2].push_back(p);
         else if (m <= 32) sliced_ids[m == 32 ? 0 : 1].push_back(p);
         else if (m <= 64) sliced_ids[m == 64 ? 2 : 3].push_back(p);
-        else sliced_ids[4].push_back(p);
+        else sliced_ids[m <= kSlicedThreeCtaLen ? 4 : 5].push_back(p);
     }
     for (int NW = 1; NW <= kMaxWords; ++NW) {
         auto &ids = by_nw[NW];
@@ -463,7 +465,7 @@ int build_lists(apm_plan *pl, const std::vector<int> &ids_in, std::vector<Bucket
         if ((rc = upload(&b.d_group_pat, b.group_pat))) return rc;
         buckets.push_back(std::move(b));
     }
-    for (int which = 0; which < 5; ++which) {
+    for (int which = 0; which < 6; ++which) {
         auto &ids = sliced_ids[which];
         if (ids.empty()) continue;
         std::stable_sort(ids.begin(), ids.end(),
@@ -838,17 +840,26 @@ int launch_sliced(apm_plan *pl, SlicedList &l, const uint8_t *d_buf, long long b
     if (pl->opt.mode != MODE_DIRECT && pl->k <= kBandMaxK && 2 * pl->k + 1 < l.mmin &&
         band_smem_need(pl, l) <= (size_t)pl->smem_optin)
         return launch_band(pl, l, a, lim - w0, st);
-    // auto: measured on B200 (profiles/r01_quick_cell_variants.jsonl) -- the FMA-pipe variants win where the whole
-    // pattern is one register block (m <= 32: 4 LOP3 + 2 IMAD, m <= 64: 4 LOP3 + 3 IMAD); register-file operand
-    // bandwidth, not the pipes, limits the co-issue (tools/ubench/pipe_mix.cu), so the gain is ~6 %
-    const int cell = pl->opt.cell >= 0 ? pl->opt.cell : (l.MC == 32 ? 2 : (l.mmax <= 64 ? 1 : 0));
-    // lengths that are not a multiple of the block width: kernels with compile-time block widths (apm_sliced.cuh)
-    if (l.ragged == 1) return l.MC == 32 ? launch_sliced_mc<32, 2, 1>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 1, 1>(pl, l, a, lim - w0, st);
-    if (cell == 2)
-        return l.MC == 32 ? launch_sliced_mc<32, 2>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 2>(pl, l, a, lim - w0, st);
-    if (cell == 1)
-        return l.MC == 32 ? launch_sliced_mc<32, 1>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 1>(pl, l, a, lim - w0, st);
-    return l.MC == 32 ? launch_sliced_mc<32, 0>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 0>(pl, l, a, lim - w0, st);
+    // auto (measured on B200, profiles/r02_cell_reuse_*.jsonl): the register-file bound of the co-issued cell decides.
+    // CELL 3 (4 LOP3 + 3 IMAD ordered for the operand reuse cache) wins for every list that runs at 3 CTAs per SM
+    // (m <= 224): m = 64 120.5 TCUPS (CELL 1: 114.2), m = 128 116.6 (CELL 0: 109.3), ragged single blocks m = 50 113.0
+    // (CELL 1: 102.7); for longer patterns (2 CTAs per SM) plain LOP3 stays ahead (m = 1000: 91.8 vs 86.4).  m = 32:
+    // CELL 3 in the two-row sweep (114.9; CELL 2 one row: 110.6); ragged m < 32: CELL 2 (CELL 3 is within +-2 %).
+    if (pl->opt.cell < 0) {
+        if (l.MC == 32) {
+            if (l.ragged == 1) return launch_sliced_mc<32, 2, 1>(pl, l, a, lim - w0, st);
+            if (l.mmin == 32 && l.mmax == 32) return launch_sliced_mc<32, 3, 3>(pl, l, a, lim - w0, st);
+            return launch_sliced_mc<32, 2>(pl, l, a, lim - w0, st);
+        }
+        if (l.ragged == 1) return launch_sliced_mc<64, 3, 1>(pl, l, a, lim - w0, st);
+        return l.mmax <= kSlicedThreeCtaLen ? launch_sliced_mc<64, 3>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 0>(pl, l, a, lim - w0, st);
+    }
+    switch (pl->opt.cell) {
+        case 3: return l.MC == 32 ? launch_sliced_mc<32, 3>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 3>(pl, l, a, lim - w0, st);
+        case 2: return l.MC == 32 ? launch_sliced_mc<32, 2>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 2>(pl, l, a, lim - w0, st);
+        case 1: return l.MC == 32 ? launch_sliced_mc<32, 1>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 1>(pl, l, a, lim - w0, st);
+        default: return l.MC == 32 ? launch_sliced_mc<32, 0>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 0>(pl, l, a, lim - w0, st);
+    }
 }
 
 // mode=filter: seed scan + verification of the filtered patterns over window starts [w0, w1) (local
@@ -1157,6 +1168,7 @@ int apm_set_option(const char *key, const char *value) {
         else if (v == "lop3") g_opt.cell = 0;
         else if (v == "fma3") g_opt.cell = 1;
         else if (v == "fma" || v == "fma2") g_opt.cell = 2;
+        else if (v == "fma3r") g_opt.cell = 3;
         else return bad();
     } else if (k == "filter_scan") {
         if (v == "auto") g_opt.filter_scan = 0;
@@ -1214,7 +1226,7 @@ const char *apm_get_option(const char *key) {
     else if (k == "rblock") tl_optbuf = o.rblock ? std::to_string(o.rblock) : "auto";
     else if (k == "tile") tl_optbuf = o.tile ? std::to_string(o.tile) : "auto";
     else if (k == "variant") tl_optbuf = std::to_string(o.variant);
-    else if (k == "cell") tl_optbuf = o.cell == 2 ? "fma" : (o.cell == 1 ? "fma3" : (o.cell == 0 ? "lop3" : "auto"));
+    else if (k == "cell") tl_optbuf = o.cell == 3 ? "fma3r" : (o.cell == 2 ? "fma" : (o.cell == 1 ? "fma3" : (o.cell == 0 ? "lop3" : "auto")));
     else if (k == "filter_scan") tl_optbuf = o.filter_scan == 1 ? "hash" : (o.filter_scan == 2 ? "dna" : "auto");
     else if (k == "tail") tl_optbuf = o.tail == 1 ? "dp" : "bitpar";
     else if (k == "reduce") tl_optbuf = o.reduce == 1 ? "nccl" : (o.reduce == 2 ? "host" : (o.reduce == 3 ? "p2p" : "auto"));

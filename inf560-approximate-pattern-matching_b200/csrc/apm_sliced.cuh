@@ -40,6 +40,7 @@ constexpr int kSlicedTile = 32 * kSlicedThreads;  // window starts per tile
 constexpr int kURowBytes = 136;                   // 34 words per U row: lanes hit distinct banks with LDS.64
 constexpr int kSlicedMaxPlanes = 8;               // symbols with their own occurrence plane
 constexpr int kSlicedMaxLen = 1024;               // longest pattern handled (column blocks of 64)
+constexpr int kSlicedThreeCtaLen = 224;            // longest pattern whose U table still lets three CTAs share an SM (4 planes)
 constexpr int kSlicedTotPlanes = 12;              // bit-planes of the running distance sum (values <= 2*1024+k)
 constexpr uint8_t kNoPlane = 0xFF;
 
@@ -95,6 +96,9 @@ constexpr int kLutNor3 = 0x01;       // ~(a | b | c)
 constexpr int kLutOrAndN = 0xF4;     // a | (b & ~c)
 constexpr int kLutXor3 = 0x96;       // a ^ b ^ c
 constexpr int kLutAndOrN = 0xD0;     // a & (b | ~c)
+constexpr int kLutNotAAndB = 0x0C;   // ~a & b
+constexpr int kLutNotAAndC = 0x0A;   // ~a & c
+constexpr int kLutCOrAAndNotB = 0xBA;  // c | (a & ~b)
 
 // c - a on the FMA pipe: IMAD with the multiplier -1 held where ptxas cannot see its value (otherwise the
 // subtraction becomes an IADD3 and goes back to the ALU pipe, the one the LOP3s saturate)
@@ -145,6 +149,7 @@ struct SumPlanes {  // adds the planes of columns 2I and 2I+1 (h+ and ~h- of eac
 // One DP cell for 32 windows.  (ap, am) = vertical delta coming from the left neighbour, (bp, bm) =
 // horizontal delta coming from the row above; both are replaced by the deltas of this cell.
 //   CELL 0: five LOP3 (all on the ALU pipe).
+//   CELL 3: CELL 1 with fewer register-file reads (see below); the default for m <= 224.
 //   CELL 1: four LOP3 + three IMAD.  With x = ~d0 (the diagonal step D[i][j] - D[i-1][j-1], one bit) the deltas
 //           obey h = x - a as integers PER BIT POSITION: h+ - h- = x - a+ + a-.  Every term is 0/1 and so is
 //           h+, hence the identity also holds for the whole 32-bit words modulo 2^32 (borrows of intermediate
@@ -171,6 +176,27 @@ __device__ __forceinline__ void sliced_cell(uint32_t q, uint32_t &ap, uint32_t &
         const uint32_t vm = lop3<kLutAndOr>(bp, q, am);
         const uint32_t vp = lop3<kLutOrAndN>(bm, x, bp);
         const uint32_t hm2 = lop3<kLutAndOr>(ap, q, bm);
+        const uint32_t t1 = fma_sub(ap, x, neg1);     // a+ - x
+        const uint32_t t2 = fma_sub(t1, hm2, neg1);   // a+ - x - h-
+        bp = fma_sub(am, t2, neg1);                   // h+ = a- - a+ + x + h-
+        bm = hm2;
+        ap = vp;
+        am = vm;
+    } else if constexpr (CELL == 3) {
+        // CELL 3 ("fma3r"): CELL 1 rewritten for the REGISTER FILE, which is what bounds the 4 LOP3 + 3 IMAD cell: it delivers
+        // ~2 operands per clock and SMSP (tools/ubench/issue_order.cu), CELL 1 reads 18 (ptxas' code: 18.4 per cell incl. the
+        // LDS address, 9.2 clk against 8 clk of ALU pipe).  (i) v- and h- are taken from x: v = -1 iff b = +1 and the diagonal
+        // step is 0 (b+ = 1 excludes b- = 1, so x = 0 <=> eq | a-), likewise h- -- two register operands instead of three.
+        // (ii) x sits in slot A of the three LOP3s and of the IMAD that consume it, b+ in slot B of v- and v+, a+ in slot C of
+        // h- and of that IMAD, so ptxas can flag them .reuse (operand reuse cache) and keeps the cell's instructions
+        // together.  ptxas' code reads 13.5 registers per cell (profiles/r02_cell_reuse_*.jsonl: m = 64 114.2 -> 120.5 TCUPS).
+        // The row recurrence a- -> a-' is two LOP3 deep here (x, then v-) instead of one; at 3 warps per scheduler the
+        // latency is hidden, and unlike the straightforward x-first code (measured: spills, 91 TCUPS) this operand order
+        // keeps ptxas from hoisting the whole chain ahead of the row.
+        const uint32_t x = lop3<kLutNor3>(q, am, bm);
+        const uint32_t vm = lop3<kLutNotAAndB>(x, bp, bp);
+        const uint32_t vp = lop3<kLutCOrAAndNotB>(x, bp, bm);
+        const uint32_t hm2 = lop3<kLutNotAAndC>(x, ap, ap);
         const uint32_t t1 = fma_sub(ap, x, neg1);     // a+ - x
         const uint32_t t2 = fma_sub(t1, hm2, neg1);   // a+ - x - h-
         bp = fma_sub(am, t2, neg1);                   // h+ = a- - a+ + x + h-
@@ -274,6 +300,55 @@ __device__ __forceinline__ void sliced_sweep(const unsigned char *__restrict__ u
 #pragma unroll
         for (int j = 0; j < MC; ++j)  // columns >= width: back to the neutral boundary value (they add a constant)
             if (j >= width) { hp[j] = 0xFFFFFFFFu; hm[j] = cell_plus_second_plane<CELL>(); }
+    }
+}
+
+// Two rows per trip, skewed by SK columns: row i at column c and row i + 1 at column c - SK are independent, so a warp
+// carries two recurrence chains instead of one.  The row chain (a- -> a-' of the right neighbour) then stops being the
+// longest dependency path of the unrolled row, ptxas keeps the cells in program order, and the cell codes that take
+// v- and h- from x (two LOP3 deep, fewer register operands) no longer blow up the live ranges.  rows must be even;
+// all MC columns are used (single full block).
+template <int MC, int CELL, int SK>
+__device__ __forceinline__ void sliced_sweep2(const unsigned char *__restrict__ urow, const uint8_t *__restrict__ pc, int rows,
+                                              uint32_t plane_bytes, uint32_t (&hp)[MC], uint32_t (&hm)[MC], uint32_t neg1) {
+    constexpr int G = 4;  // columns per pipeline group and row: 2 + 2 LDS.64 in flight
+    constexpr int NS = MC + SK;  // steps per row pair
+    static_assert(SK % G == 0 && SK >= G, "skew must be a multiple of the group size");
+    const unsigned char *eA = urow + (uint32_t)__ldg(pc) * plane_bytes;
+    const unsigned char *eB = urow + (uint32_t)__ldg(pc + 1) * plane_bytes;
+    uint32_t codeA = __ldg(pc + 2), codeB = __ldg(pc + 3);
+    uint2 bufA[G / 2], bufB[G / 2];
+#pragma unroll
+    for (int q = 0; q < G / 2; ++q) bufA[q] = *reinterpret_cast<const uint2 *>(eA + q * 8);
+#pragma unroll 1
+    for (int i = 0; i < rows; i += 2) {
+        const unsigned char *eA_next = urow + codeA * plane_bytes;
+        const unsigned char *eB_next = urow + codeB * plane_bytes;
+        codeA = __ldg(pc + i + 4);
+        codeB = __ldg(pc + i + 5);
+        uint32_t apA = 0xFFFFFFFFu, amA = 0u, apB = 0xFFFFFFFFu, amB = 0u;
+#pragma unroll
+        for (int s0 = 0; s0 < NS; s0 += G) {
+            // current words: row A columns [s0, s0 + G), row B columns [s0 - SK, s0 - SK + G)
+            uint2 curA[G / 2], curB[G / 2];
+#pragma unroll
+            for (int q = 0; q < G / 2; ++q) { curA[q] = bufA[q]; curB[q] = bufB[q]; }
+            const int nA = s0 + G, nB = s0 + G - SK;  // first columns of the next group
+#pragma unroll
+            for (int q = 0; q < G / 2; ++q) {
+                if (nA < MC) bufA[q] = *reinterpret_cast<const uint2 *>(eA + ((nA + 2 * q) >> 5) * kURowBytes + ((nA + 2 * q) & 31) * 4);
+                else if (nA == NS) bufA[q] = *reinterpret_cast<const uint2 *>(eA_next + q * 8);
+                if (nB >= 0 && nB < MC) bufB[q] = *reinterpret_cast<const uint2 *>(eB + ((nB + 2 * q) >> 5) * kURowBytes + ((nB + 2 * q) & 31) * 4);
+            }
+#pragma unroll
+            for (int cc = 0; cc < G; ++cc) {
+                const int cA = s0 + cc, cB = s0 + cc - SK;
+                if (cA < MC) sliced_cell<CELL>((cc & 1) ? curA[cc >> 1].y : curA[cc >> 1].x, apA, amA, hp[cA], hm[cA], neg1);
+                if (cB >= 0 && cB < MC) sliced_cell<CELL>((cc & 1) ? curB[cc >> 1].y : curB[cc >> 1].x, apB, amB, hp[cB], hm[cB], neg1);
+            }
+        }
+        eA = eA_next;
+        eB = eB_next;
     }
 }
 
@@ -420,9 +495,10 @@ __device__ __forceinline__ TileGeom sliced_stage_tile(const SlicedArgs &a, long 
 // RG = 0: any pattern lengths, ragged blocks through the run-time-width sweep (the round-1 kernel, unchanged).
 // RG = 1: single-block patterns (m <= MC) swept with the compile-time width m rounded up to a multiple of 4
 //         (m = 50: 93.8 -> 103.3 TCUPS, m = 20: 76.6 -> 99.2; profiles/r02_len_sweep.txt).
-// The host keeps lengths that are multiples of MC, and all multi-block patterns, on RG = 0 (its register allocation
-// is what the headline number was tuned on) and routes single-block ragged lengths to RG = 1 when the cell code is
-// chosen automatically.  (A variant with compile-time widths for the LAST block of multi-block patterns was built
+// RG = 3: lists with m == MC, two skewed rows per trip (sliced_sweep2); used for m = 32 (110.6 -> 114.9 TCUPS with CELL 3;
+//         at m = 64 the one-row sweep is faster: 120.5 vs 116.3).
+// The host keeps m = 64 and all multi-block patterns on RG = 0 and routes single-block ragged lengths to RG = 1, m = 32
+// to RG = 3, when the cell code is chosen automatically.  (A variant with compile-time widths for the LAST block of multi-block patterns was built
 // and measured 3-10 % SLOWER than the run-time-width sweep for every m > 64 -- the extra sweep instantiations cost
 // the multi-block kernel its register allocation -- and was dropped.)
 template <int MC, int CELL, int RG = 0>
@@ -492,7 +568,10 @@ __global__ void __launch_bounds__(kSlicedThreads, MC == 64 ? 3 : 4) sliced_count
                     uint32_t hp[MC], hm[MC];
 #pragma unroll
                     for (int j = 0; j < MC; ++j) { hp[j] = 0xFFFFFFFFu; hm[j] = cell_plus_second_plane<CELL>(); }  // D[0][j] - D[0][j-1] = +1
-                    if constexpr (RG == 1) {
+                    if constexpr (RG == 3) {
+                        // two skewed rows per trip; the host routes only lists with m == MC (even) here
+                        sliced_sweep2<MC, CELL, 4>(ub, pc, m, plane_bytes, hp, hm, neg1);
+                    } else if constexpr (RG == 1) {
                         sliced_sweep_dispatch<MC, CELL, 4, false, (MC == 64 ? 36 : 4)>((width + 3) & ~3, ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);
                     } else if (MC == 32 || nblk == 1) {
                         if (width == MC) sliced_sweep<MC, CELL, true, false, false>(ub, pc, m, width, plane_bytes, hp, hm, vs, vstride, neg1);

@@ -45,11 +45,12 @@ def test_golden_host_api(case, kernel):
 
 
 @pytest.mark.parametrize("mode", ["direct", "band"])
-@pytest.mark.parametrize("cell", ["auto", "lop3", "fma3", "fma"])
+@pytest.mark.parametrize("cell", ["auto", "lop3", "fma3", "fma", "fma3r"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: c["name"])
 def test_golden_both_cell_codes(case, cell, mode):
     """The DP cell as 5 LOP3 (lop3), 4 LOP3 + 3 FMA-pipe subtractions (fma3), 4 LOP3 + 2 subtractions on the
-    (minus, nonzero) / (plus, nonzero) delta encoding (fma); auto picks per pattern-length class."""
+    (minus, nonzero) / (plus, nonzero) delta encoding (fma), the 4 + 3 cell ordered for the operand reuse cache with
+    v- / h- taken from x (fma3r); auto picks per pattern-length class."""
     apm_b200.set_option("kernel", "sliced")
     apm_b200.set_option("cell", cell)
     apm_b200.set_option("mode", mode)
@@ -74,7 +75,7 @@ def test_cell_codes_agree_on_random_slabs(seed):
     k = int(rng.integers(0, 7))
     out = {}
     for mode in ("direct", "band"):
-        for cell in ("lop3", "fma3", "fma"):
+        for cell in ("lop3", "fma3", "fma", "fma3r"):
             apm_b200.set_option("mode", mode)
             apm_b200.set_option("cell", cell)
             out[(mode, cell)] = apm_b200.count_matches(text, pats, k)
@@ -780,3 +781,100 @@ def test_band_kernel_too_wide_for_shared_memory_falls_back(mode):
         want = apm_b200.count_matches(text, pats, k)
         apm_b200.set_option("kernel", "auto"); apm_b200.set_option("mode", mode)
         assert apm_b200.count_matches(text, pats, k) == want
+
+
+# ---------------------------------------------------------------------------------------------
+# threaded host: the one-shot C-ABI call is re-entrant
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["direct", "filter"])
+def test_concurrent_host_threads(mode):
+    """Four host threads call apm_count_matches at the same time (ctypes releases the GIL), each with its own text
+    and pattern set; every result must equal the serial oracle.  Exercises the device-block cache, the pooled
+    pinned buffers, the per-kernel shared-memory opt-in table and the option snapshot under contention."""
+    import threading
+
+    apm_b200.set_option("mode", mode)
+    jobs = []
+    for t in range(4):
+        rng = np.random.default_rng(9100 + t)
+        n = 300_000 + 50_000 * t
+        text = oracle.synth_text(0x5EED0001, 7777 * t, n).tobytes()
+        pats = []
+        for m in (20, 32, 50, 64, 64, 100, 200)[: 4 + t % 4]:
+            off = int(rng.integers(0, n - m))
+            p = bytearray(text[off:off + m])
+            for s in range(int(rng.integers(0, 4))):
+                p[int(rng.integers(0, m))] = ord("ACGT"[int(rng.integers(0, 4))])
+            pats.append(bytes(p))
+        pats.append(text[-30:] + b"ACGTACGTAC")  # truncated tail windows
+        jobs.append((text, pats, 3))
+    want = [oracle.count_matches(text, pats, k) for text, pats, k in jobs]
+    got = [None] * len(jobs)
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                got[i] = apm_b200.count_matches(*jobs[i])
+        except Exception as e:  # noqa: BLE001
+            errs.append((i, repr(e)))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    assert got == want
+
+
+# ---------------------------------------------------------------------------------------------
+# automatic kernel routing of the direct mode: every list class against the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cell", ["auto", "fma3r"])
+def test_auto_routing_all_length_classes(cell):
+    """auto: m = 32 -> two-row sweep (RG 3), ragged m < 32 / 33..63 -> compile-time widths (RG 1), m = 64 and 65..224 ->
+    CELL 3, longer -> CELL 0 -- one pattern set that populates every list, planted copies with substitutions and
+    indels so that hits exist, k = 0, 3, 5; fma3r: the same set through the generic kernel with CELL 3."""
+    apm_b200.set_option("kernel", "sliced")
+    apm_b200.set_option("cell", cell)
+    rng = np.random.default_rng(31337)
+    n = 150_000
+    text = bytearray(oracle.synth_text(0x5EED0001, 4242, n).tobytes())
+    pats = []
+    for m in (32, 64, 64, 32, 50, 64, 100, 64, 32, 64, 20, 31, 33, 63, 65, 128, 200, 224, 225, 300):
+        off = int(rng.integers(0, n - m - 8))
+        p = bytearray(text[off:off + m + 4])
+        for s_ in range(int(rng.integers(0, 5))):
+            pos = int(rng.integers(0, m))
+            kind = int(rng.integers(0, 3))
+            if kind == 0:
+                p[pos] = ord("ACGT"[int(rng.integers(0, 4))])
+            elif kind == 1:
+                del p[pos]
+            else:
+                p.insert(pos, ord("ACGT"[int(rng.integers(0, 4))]))
+        pats.append(bytes(p[:m]))
+    pats.append(bytes(text[-64:]))
+    pats.append(bytes(text[-32:]))
+    for k in (0, 3, 5):
+        got = apm_b200.count_matches(bytes(text), pats, k)
+        assert got == oracle.count_matches(bytes(text), pats, k), (cell, k)
+
+
+def test_all_m32_and_all_m64_sets():
+    """pattern sets of a single length (the lists the two-row sweep and the m = 64 kernel take alone), odd pattern
+    counts, a text shorter than one tile and one that ends inside a tile"""
+    rng = np.random.default_rng(99)
+    for n in (3000, 70_001):
+        text = oracle.synth_text(0x5EED0001, 11 * n, n).tobytes()
+        for m in (32, 64):
+            pats = []
+            for i in range(7):
+                off = int(rng.integers(0, n - m))
+                p = bytearray(text[off:off + m])
+                for s_ in range(i % 4):
+                    p[int(rng.integers(0, m))] = ord("ACGT"[int(rng.integers(0, 4))])
+                pats.append(bytes(p))
+            for k in (0, 2, 4):
+                assert apm_b200.count_matches(text, pats, k) == oracle.count_matches(text, pats, k), (n, m, k)

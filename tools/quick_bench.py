@@ -34,7 +34,7 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     combos = []
     for mode in ("direct", "band"):
-      for cell in ("lop3", "fma3", "fma"):
+      for cell in ("lop3", "fma3", "fma", "fma3r"):
         combos.append((64, 4, 256, "4", "512", 16 << 20, "0", "auto", mode, cell))
         combos.append((200, 10, 64, "1", "512", 4 << 20, "0", "auto", mode, cell))
         combos.append((32, 2, 256, "4", "512", 32 << 20, "0", "auto", mode, cell))

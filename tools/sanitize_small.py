@@ -23,7 +23,7 @@ apm_b200.set_option("kernel", "auto")
 text = oracle.synth_text(0x5EED0001, 5, 20000).tobytes()
 pats = [text[100:164], text[3000:3300], text[9000:9033], text[-20:] + b"ACGTAC"]
 want = oracle.count_matches(text, pats, 3)
-for cell in ("lop3", "fma3", "fma"):
+for cell in ("lop3", "fma3", "fma", "fma3r"):
     apm_b200.set_option("cell", cell)
     got = apm_b200.count_matches(text, pats, 3)
     ok &= got == want

@@ -49,7 +49,7 @@ for c in range(cases):
     apm_b200.set_option("kernel", "auto")
     for mode, extra in (("filter", {}), ("filter", {"filter_cand_mb": "1"}), ("band", {}), ("direct", {})):
         apm_b200.set_option("mode", mode)
-        apm_b200.set_option("cell", str(rng.choice(["auto", "lop3", "fma3", "fma"])))
+        apm_b200.set_option("cell", str(rng.choice(["auto", "lop3", "fma3", "fma", "fma3r"])))
         for kk, vv in extra.items(): apm_b200.set_option(kk, vv)
         got, hits, _ = apm_b200.find_matches(text, pats, k, max_hits=1 << 22)
         for kk in extra: apm_b200.set_option(kk, "128")

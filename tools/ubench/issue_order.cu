@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(128, WPS) order_kernel(uint32_t *out, int iter
 #pragma unroll
     for (int i = 0; i < NR; ++i) r[i] = seed * (i + 1) + threadIdx.x;
     const uint32_t mulv = mul_u | (threadIdx.x >> 20);
+    const uint32_t fx = seed ^ (threadIdx.x * 77u), fy = seed + threadIdx.x * 1234567u;  // fixed source registers
     int n = 0;
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
@@ -85,9 +86,12 @@ __global__ void __launch_bounds__(128, WPS) order_kernel(uint32_t *out, int iter
                 const int idx = g * L + l;
                 const int d = idx % NR;  // d last written NR instrs ago
                 const int s1 = LD >= 2 ? (idx + O1) % NR : d, s2 = LD >= 3 ? (idx + O2) % NR : s1;
+                (void)s2;
                 const int i1 = IDR >= 2 ? (idx + O1) % NR : d;
                 const char c = pat.s[l];
-                if (c == 'L') r[d] = lop3(r[d], r[s1], r[s2]);
+                if (c == 'L' && LD == 4) r[d] = lop3(fx, fy, r[d]);
+                else if (c == 'L' && LD == 5) r[d] = lop3(fx, r[d], r[s1]);
+                else if (c == 'L') r[d] = lop3(r[d], r[s1], r[s2]);
                 else if (c == 'I') r[d] = imad(r[i1], mul_u, r[d]);
                 else if (c == 'J') r[d] = imad(r[i1], mulv, r[d]);
                 else if (c == 'F') r[d] = ffma(r[s1], r[s2], r[d]);
@@ -138,11 +142,10 @@ void run() {
 
 template <int ID> void run_all() { run<ID, 3>(); }
 template <int ID> void sweep() {
-    run<ID, 3, 13, 26, 3, 2>(); run<ID, 3, 13, 26, 2, 2>(); run<ID, 3, 13, 26, 1, 2>(); run<ID, 3, 13, 26, 3, 1>();
-    run<ID, 3, 13, 26, 1, 1>(); run<ID, 3, 14, 28, 3, 2>(); run<ID, 3, 1, 2, 3, 2>(); run<ID, 3, 2, 4, 3, 2>();
-    run<ID, 3, 4, 8, 3, 2>(); run<ID, 3, 8, 16, 3, 2>(); run<ID, 3, 1, 3, 3, 2>(); run<ID, 3, 2, 1, 3, 2>();
+    run<ID, 3, 13, 26, 3, 2>(); run<ID, 3, 13, 26, 4, 2>(); run<ID, 3, 13, 26, 5, 2>(); run<ID, 3, 13, 26, 2, 2>();
+    run<ID, 1, 13, 26, 3, 2>(); run<ID, 1, 13, 26, 4, 2>(); run<ID, 1, 13, 26, 5, 2>(); run<ID, 1, 13, 26, 2, 2>();
 }
 int main() {
-    sweep<0>(); sweep<2>(); sweep<15>(); sweep<8>(); sweep<3>(); sweep<5>(); sweep<7>(); sweep<22>();
+    sweep<0>(); sweep<8>(); sweep<3>(); sweep<5>(); sweep<7>();
     return 0;
 }
