@@ -142,10 +142,10 @@ void run() {
 
 template <int ID> void run_all() { run<ID, 3>(); }
 template <int ID> void sweep() {
-    run<ID, 3, 13, 26, 3, 2>(); run<ID, 3, 13, 26, 4, 2>(); run<ID, 3, 13, 26, 5, 2>(); run<ID, 3, 13, 26, 2, 2>();
-    run<ID, 1, 13, 26, 3, 2>(); run<ID, 1, 13, 26, 4, 2>(); run<ID, 1, 13, 26, 5, 2>(); run<ID, 1, 13, 26, 2, 2>();
+    run<ID, 3, 1, 26, 2, 2>(); run<ID, 3, 2, 26, 2, 2>(); run<ID, 3, 3, 26, 2, 2>(); run<ID, 3, 4, 26, 2, 2>();
+    run<ID, 3, 6, 26, 2, 2>(); run<ID, 3, 8, 26, 2, 2>(); run<ID, 3, 13, 26, 2, 2>(); run<ID, 3, 16, 26, 2, 2>();
 }
 int main() {
-    sweep<0>(); sweep<8>(); sweep<3>(); sweep<5>(); sweep<7>();
+    sweep<15>(); sweep<8>(); sweep<3>();
     return 0;
 }
