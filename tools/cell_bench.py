@@ -26,10 +26,12 @@ def main():
     apm_b200.synth_text_device(text.data_ptr(), TEXT_SEED, 0, n)
     torch.cuda.synchronize()
     st = torch.cuda.current_stream().cuda_stream
-    apm_b200.set_option("mode", "direct")
+    apm_b200.set_option("mode", sys.argv[3] if len(sys.argv) > 3 else "direct")
     for m in lens:
         P = 256 if m <= 64 else 64
         slab = max((1 << 40) // (P * m * m), 1 << 19) // 4096 * 4096
+        if len(sys.argv) > 3 and sys.argv[3] == "band":
+            slab *= 4
         pats, _, _ = make_patterns(TEXT_SEED, n, P, m, 7)
         ref = None
         for cell in cells:
