@@ -30,6 +30,16 @@ __device__ __forceinline__ uint32_t iadd3(uint32_t a, uint32_t b, uint32_t c) {
     return d;
 }
 
+__device__ __forceinline__ uint32_t shfw(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm volatile("shf.r.wrap.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
 struct Pat { char s[24]; };
 template <int N> constexpr Pat mk(const char (&x)[N]) { Pat p{}; for (int i = 0; i < N; ++i) p.s[i] = x[i]; return p; }
 constexpr int plen(const Pat &p) { int n = 0; while (p.s[n]) ++n; return n; }
@@ -62,6 +72,13 @@ DEFPAT(22, "LLLLI")
 DEFPAT(23, "IF")
 DEFPAT(24, "LIF")
 DEFPAT(25, "LLIF")
+DEFPAT(26, "SSSS")
+DEFPAT(27, "HHHH")
+DEFPAT(28, "SH")
+DEFPAT(29, "SSH")
+DEFPAT(30, "SSSSH")
+DEFPAT(31, "SSSSHI")
+DEFPAT(32, "LLLLH")
 
 // O1, O2: register-index offsets of the 2nd / 3rd source; LD = distinct source registers of a LOP3 (1..3);
 // IDR = distinct source registers of an IMAD (1..2, plus the uniform multiplier)
@@ -96,6 +113,8 @@ __global__ void __launch_bounds__(128, WPS) order_kernel(uint32_t *out, int iter
                 else if (c == 'J') r[d] = imad(r[i1], mulv, r[d]);
                 else if (c == 'F') r[d] = ffma(r[s1], r[s2], r[d]);
                 else if (c == 'A') r[d] = iadd3(r[d], r[s1], r[s2]);
+                else if (c == 'S') r[d] = shfw(r[d], r[s1], r[s1]);
+                else if (c == 'H') r[d] = mulhi(r[d], mul_u);
             }
         }
         ++n;
@@ -131,7 +150,7 @@ void run() {
         if (ms < best) best = ms;
     }
     int nl = 0, ni = 0;
-    for (int i = 0; i < L; ++i) { if (pat.s[i] == 'L' || pat.s[i] == 'A') ++nl; else ++ni; }
+    for (int i = 0; i < L; ++i) { if (pat.s[i] == 'L' || pat.s[i] == 'A' || pat.s[i] == 'S') ++nl; else ++ni; }
     const double groups = (double)iters * REP * WPS;  // per SMSP
     const double clk = best * 1e-3 * 1.965e9;
     printf("o1=%2d o2=%2d LD=%d ID=%d  ", O1, O2, LD, IDR);
@@ -141,11 +160,8 @@ void run() {
 }
 
 template <int ID> void run_all() { run<ID, 3>(); }
-template <int ID> void sweep() {
-    run<ID, 3, 1, 26, 2, 2>(); run<ID, 3, 2, 26, 2, 2>(); run<ID, 3, 3, 26, 2, 2>(); run<ID, 3, 4, 26, 2, 2>();
-    run<ID, 3, 6, 26, 2, 2>(); run<ID, 3, 8, 26, 2, 2>(); run<ID, 3, 13, 26, 2, 2>(); run<ID, 3, 16, 26, 2, 2>();
-}
+template <int ID> void sweep() { run<ID, 3, 13, 26, 2, 2>(); run<ID, 8, 13, 26, 2, 2>(); }
 int main() {
-    sweep<15>(); sweep<8>(); sweep<3>();
+    sweep<26>(); sweep<27>(); sweep<28>(); sweep<29>(); sweep<30>(); sweep<31>(); sweep<32>(); sweep<2>();
     return 0;
 }
