@@ -94,9 +94,10 @@ int apm_find_matches(const unsigned char *text, size_t n_bytes, const char *cons
  *   "ingest_threads" = "auto" | 1..64   reader threads PER GPU of the chunked ingest (files and large pageable host
  *                 buffers: pread / memcpy into pinned staging buffers, async H2D, counting overlapped); auto =
  *                 host threads / GPUs, at most 8
- *   "cell"    = "auto" | "lop3" | "fma3" | "fma"   code of one DP cell in the window-sliced / band kernels:
+ *   "cell"    = "auto" | "lop3" | "fma3" | "fma" | "fma3r"   code of one DP cell in the window-sliced / band kernels:
  *                 lop3: 5 LOP3 (ALU pipe only); fma3: 4 LOP3 + 3 IMAD; fma: 4 LOP3 + 2 IMAD (FMA pipe takes the
- *                 subtractions); auto (default) picks per pattern-length class.  Same results, different speed.
+ *                 subtractions); fma3r: 4 LOP3 + 3 IMAD with the operands ordered for the register file's reuse cache;
+ *                 auto (default) picks per pattern-length class (fma3r for m <= 224).  Same results, different speed.
  *   "reduce"  = "auto" | "p2p" | "nccl" | "host"   how the per-GPU count vectors of the one-shot API are combined
  *                 when "gpus" > 1: p2p = GPU 0 pulls every other GPU's vector through NVLink peer memory and adds it to
  *                 its own (our own kernel, stream ordered, no communicator, no cross-device atomics); nccl = one in-place ncclAllReduce per device (NCCL
