@@ -470,6 +470,39 @@ def run_ours(args) -> None:
                 "counts_equal_direct_on_slab": bool(slab_same),
                 "note": "complete config-5 job (2^34 B x 4096 patterns, every window start of every rank's shard + "
                         "count all-reduce) in exact filter mode; the truncated tail windows go through the DP kernel"}
+        # the same job with a resident 2-bit copy of the text (packed once, outside the timed region: the repeated-search
+        # case -- database in HBM, query batches change)
+        try:
+            pk = torch.empty(apm_b200.text_pack_bytes(b1 - b0), dtype=torch.uint8, device=dev)
+            p_e0, p_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p_e0.record()
+            apm_b200.text_pack_device(shard.data_ptr(), b1 - b0, pk.data_ptr(), stream)
+            p_e1.record()
+            whole = fplan.read_counts(stream)
+            fplan.zero_counts(stream)
+            sync_all()
+            q_e0, q_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q_e0.record()
+            fplan.count_device_packed(shard.data_ptr(), pk.data_ptr(), b0, b1 - b0, N_TOTAL, j0, j1, stream)
+            if world > 1:
+                reduced.copy_(_tensor_from_ptr(torch, fplan.counts_device_ptr(), NB_PATTERNS, dev))
+                dist.all_reduce(reduced, op=dist.ReduceOp.SUM)
+            q_e1.record()
+            sync_all()
+            pms = q_e0.elapsed_time(q_e1)
+            same = fplan.read_counts(stream) == whole
+            if world > 1:
+                t = torch.tensor([pms, 0.0 if same else 1.0], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                pms, same = float(t[0].item()), float(t[1].item()) == 0.0
+            filt["packed_text"] = {"full_job_ms": pms, "text_symbols_per_s": N_TOTAL / (pms * 1e-3),
+                                   "pack_ms": p_e0.elapsed_time(p_e1), "packed_bytes_per_rank": int(pk.numel()),
+                                   "counts_equal_unpacked": bool(same),
+                                   "note": "apm_plan_count_device_packed: the scan streams the resident 2-bit copy "
+                                           "(0.25 B per symbol); verification still reads the raw bytes"}
+            del pk
+        except Exception as e:  # noqa: BLE001
+            filt["packed_text"] = {"error": repr(e)}
         fplan.close()
         apm_b200.set_option("mode", "direct")
 

@@ -141,6 +141,20 @@ int apm_plan_count_device(apm_plan *plan, const unsigned char *d_buf,
                           unsigned long long n_total, unsigned long long j_begin,
                           unsigned long long j_end, void *stream);
 
+/* Resident 2-bit copy of a device text for REPEATED searches (a database that stays in HBM while query batches
+ * change): apm_text_pack_device writes apm_text_pack_bytes(buf_len) bytes to d_packed -- word w holds the 2-bit codes
+ * ((byte >> 1) & 3) of d_buf[16 w, 16 w + 16); d_buf must be 16-byte aligned.  apm_plan_count_device_packed is
+ * apm_plan_count_device with that copy of exactly the same d_buf / buf_len at hand: in filter mode the 2-bit q-gram
+ * scan (ACGT pattern sets) then streams a quarter of the bytes and skips the packing; every other kernel, and the
+ * byte-exact verification, still read d_buf, so the text may contain any bytes and the counts are identical.
+ * d_packed = NULL makes it the plain call.                                                          */
+unsigned long long apm_text_pack_bytes(unsigned long long buf_len);
+int apm_text_pack_device(const unsigned char *d_buf, unsigned long long buf_len, void *d_packed, void *stream);
+int apm_plan_count_device_packed(apm_plan *plan, const unsigned char *d_buf, const void *d_packed,
+                                 unsigned long long buf_offset, unsigned long long buf_len,
+                                 unsigned long long n_total, unsigned long long j_begin,
+                                 unsigned long long j_end, void *stream);
+
 /* Restrict the plan to the patterns p with p % world == rank (pattern sharding, mirrors
  * src/patterns_over_ranks.c:161); counters of the other patterns stay 0.  world = 1 resets.      */
 int apm_plan_set_pattern_shard(apm_plan *plan, int rank, int world);

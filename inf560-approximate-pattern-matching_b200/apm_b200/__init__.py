@@ -28,6 +28,7 @@ EXPORTS = [
     "apm_plan_set_pattern_shard", "apm_plan_zero_counts", "apm_plan_counts_device_ptr",
     "apm_plan_read_counts", "apm_plan_max_pattern_len", "apm_synth_text_device", "apm_int_peak",
     "apm_launch_count", "apm_version", "apm_release_cache", "apm_find_matches", "apm_plan_set_hit_buffer",
+    "apm_text_pack_bytes", "apm_text_pack_device", "apm_plan_count_device_packed",
 ]
 
 
@@ -61,6 +62,10 @@ def lib():
     L.apm_plan_create.argtypes = [vp, vp, C.c_int, C.c_int, vp]
     L.apm_plan_destroy.argtypes = [vp]
     L.apm_plan_count_device.argtypes = [vp, vp, ull, ull, ull, ull, ull, vp]
+    L.apm_plan_count_device_packed.argtypes = [vp, vp, vp, ull, ull, ull, ull, ull, vp]
+    L.apm_text_pack_bytes.argtypes = [ull]
+    L.apm_text_pack_bytes.restype = ull
+    L.apm_text_pack_device.argtypes = [vp, ull, vp, vp]
     L.apm_plan_set_pattern_shard.argtypes = [vp, C.c_int, C.c_int]
     L.apm_plan_zero_counts.argtypes = [vp, vp]
     L.apm_find_matches.argtypes = [vp, C.c_size_t, vp, vp, C.c_int, C.c_int, vp, ull, vp, vp, vp]
@@ -208,6 +213,12 @@ class Plan:
         _check(lib().apm_plan_count_device(self._h, C.c_void_p(d_buf), buf_offset, buf_len, n_total,
                                            j_begin, j_end, C.c_void_p(stream)))
 
+    def count_device_packed(self, d_buf: int, d_packed: int, buf_offset: int, buf_len: int, n_total: int, j_begin: int,
+                            j_end: int, stream: int = 0) -> None:
+        """count_device with the resident 2-bit copy of the same buffer (text_pack_device) at hand."""
+        _check(lib().apm_plan_count_device_packed(self._h, C.c_void_p(d_buf), C.c_void_p(d_packed), buf_offset, buf_len,
+                                                  n_total, j_begin, j_end, C.c_void_p(stream)))
+
     def counts_device_ptr(self) -> int:
         p = C.c_void_p(None)
         _check(lib().apm_plan_counts_device_ptr(self._h, C.byref(p)))
@@ -221,6 +232,16 @@ class Plan:
 
 def synth_text_device(d_out: int, seed: int, offset: int, count: int, stream: int = 0) -> None:
     _check(lib().apm_synth_text_device(C.c_void_p(d_out), seed, offset, count, C.c_void_p(stream)))
+
+
+def text_pack_bytes(buf_len: int) -> int:
+    """bytes of the resident 2-bit copy of a text buffer of buf_len bytes"""
+    return int(lib().apm_text_pack_bytes(buf_len))
+
+
+def text_pack_device(d_buf: int, buf_len: int, d_packed: int, stream: int = 0) -> None:
+    """d_packed <- 2-bit copy of the 16-byte aligned device buffer d_buf (for Plan.count_device_packed)"""
+    _check(lib().apm_text_pack_device(C.c_void_p(d_buf), buf_len, C.c_void_p(d_packed), C.c_void_p(stream)))
 
 
 def int_peak(kind: int = 0) -> tuple[float, float]:

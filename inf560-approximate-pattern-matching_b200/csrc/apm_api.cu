@@ -875,7 +875,7 @@ cudaError_t launch_filter_scan(const FilterArgs &a, unsigned blocks, cudaStream_
 }
 
 int launch_filter(apm_plan *pl, const uint8_t *d_buf, long long buf_len, long long n_end, long long w0, long long w1,
-                  cudaStream_t st) {
+                  cudaStream_t st, const uint32_t *d_packed = nullptr) {
     FilterSet &f = pl->filter;
     const long long lim = std::min(w1, n_end - f.mmin + 1);  // full windows only
     if (f.ids.empty() || lim <= w0) return APM_OK;
@@ -883,6 +883,7 @@ int launch_filter(apm_plan *pl, const uint8_t *d_buf, long long buf_len, long lo
         // 2-bit q-gram scan + seed-hit verification (apm_dna.cuh): rounds of 2^34 window starts (35-bit positions)
         DnaRun r;
         r.buf = d_buf;
+        r.packed = d_packed;
         r.buf_len = buf_len;
         r.n_end = n_end;
         r.k = pl->k;
@@ -1382,9 +1383,10 @@ int apm_plan_max_pattern_len(apm_plan *pl, int *m_max) {
     return APM_OK;
 }
 
-int apm_plan_count_device(apm_plan *pl, const unsigned char *d_buf, unsigned long long buf_offset,
-                          unsigned long long buf_len, unsigned long long n_total, unsigned long long j_begin,
-                          unsigned long long j_end, void *stream) {
+namespace {
+int plan_count_device_impl(apm_plan *pl, const unsigned char *d_buf, const uint32_t *d_packed, unsigned long long buf_offset,
+                           unsigned long long buf_len, unsigned long long n_total, unsigned long long j_begin,
+                           unsigned long long j_end, void *stream) {
     if (!pl) return fail(APM_EINVAL, "plan is NULL");
     if (n_total > (1ull << 62) || buf_offset > n_total || buf_len > n_total - buf_offset)
         return fail(APM_EINVAL, "buffer [%llu, +%llu) is not inside the text of %llu bytes", buf_offset, buf_len, n_total);
@@ -1418,10 +1420,40 @@ int apm_plan_count_device(apm_plan *pl, const unsigned char *d_buf, unsigned lon
     }
     if (!rc)
         rc = launch_filter(pl, d_buf, (long long)buf_len, N - (long long)buf_offset, jb - (long long)buf_offset,
-                           je - (long long)buf_offset, st);
+                           je - (long long)buf_offset, st, d_packed);
     if (!rc) rc = launch_dp(pl, d_buf, (long long)buf_offset, N, jb, je, st);
     if (cur != pl->device) cudaSetDevice(cur);
     return rc;
+}
+}  // namespace
+
+int apm_plan_count_device(apm_plan *pl, const unsigned char *d_buf, unsigned long long buf_offset,
+                          unsigned long long buf_len, unsigned long long n_total, unsigned long long j_begin,
+                          unsigned long long j_end, void *stream) {
+    return plan_count_device_impl(pl, d_buf, nullptr, buf_offset, buf_len, n_total, j_begin, j_end, stream);
+}
+
+// ---- resident 2-bit copy of a device text (filter mode, ACGT pattern sets): packed once, scanned many times
+unsigned long long apm_text_pack_bytes(unsigned long long buf_len) { return 4ull * dna_pack_words(buf_len); }
+
+int apm_text_pack_device(const unsigned char *d_buf, unsigned long long buf_len, void *d_packed, void *stream) {
+    int ndev = 0;
+    if (int rc = device_ready(&ndev)) return rc;
+    if (!d_buf || !d_packed) return fail(APM_EINVAL, "d_buf / d_packed is NULL");
+    if ((reinterpret_cast<uintptr_t>(d_buf) & 15) || (reinterpret_cast<uintptr_t>(d_packed) & 3))
+        return fail(APM_EINVAL, "apm_text_pack_device: d_buf must be 16-byte aligned, d_packed 4-byte aligned");
+    CUDA_TRY(dna_pack_text(d_buf, buf_len, reinterpret_cast<uint32_t *>(d_packed), (cudaStream_t)stream));
+    g_launches++;
+    return APM_OK;
+}
+
+int apm_plan_count_device_packed(apm_plan *pl, const unsigned char *d_buf, const void *d_packed,
+                                 unsigned long long buf_offset, unsigned long long buf_len, unsigned long long n_total,
+                                 unsigned long long j_begin, unsigned long long j_end, void *stream) {
+    if (d_packed && (reinterpret_cast<uintptr_t>(d_buf) & 15))
+        return fail(APM_EINVAL, "apm_plan_count_device_packed: d_buf must be the 16-byte aligned buffer the copy was packed from");
+    return plan_count_device_impl(pl, d_buf, reinterpret_cast<const uint32_t *>(d_packed), buf_offset, buf_len, n_total,
+                                  j_begin, j_end, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------

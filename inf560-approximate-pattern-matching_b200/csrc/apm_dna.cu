@@ -36,13 +36,17 @@ cudaError_t ensure_smem(Fn fn, size_t bytes) {
     return e;
 }
 
+template <int H, bool PACKED>
+cudaError_t launch_scan_p(const DnaArgs &a, unsigned blocks, cudaStream_t st) {
+    const size_t smem = dna_smem_bytes(a.table_words, H);
+    const cudaError_t e = ensure_smem(dna_scan_kernel<H, PACKED>, smem);
+    if (e != cudaSuccess) return e;
+    dna_scan_kernel<H, PACKED><<<blocks, kDnaThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
 template <int H>
 cudaError_t launch_scan(const DnaArgs &a, unsigned blocks, cudaStream_t st) {
-    const size_t smem = dna_smem_bytes(a.table_words, H);
-    const cudaError_t e = ensure_smem(dna_scan_kernel<H>, smem);
-    if (e != cudaSuccess) return e;
-    dna_scan_kernel<H><<<blocks, kDnaThreads, smem, st>>>(a);
-    return cudaGetLastError();
+    return a.packed ? launch_scan_p<H, true>(a, blocks, st) : launch_scan_p<H, false>(a, blocks, st);
 }
 
 }  // namespace
@@ -161,9 +165,19 @@ void dna_free(DnaSet *s) {
     *s = DnaSet();
 }
 
+unsigned long long dna_pack_words(unsigned long long buf_len) { return (buf_len + 15) / 16 + 1; }
+
+cudaError_t dna_pack_text(const uint8_t *d_buf, unsigned long long buf_len, uint32_t *d_packed, cudaStream_t st) {
+    const long long nwords = (long long)dna_pack_words(buf_len);
+    const unsigned blocks = (unsigned)std::min<long long>((nwords + 255) / 256, 148ll * 32);
+    dna_pack_kernel<<<blocks, 256, 0, st>>>(d_buf, (long long)buf_len, d_packed, nwords);
+    return cudaGetLastError();
+}
+
 cudaError_t dna_launch(const DnaSet &s, const DnaRun &r, cudaStream_t st, int *launches) {
     DnaArgs a;
     a.buf = r.buf;
+    a.packed = r.packed;
     a.buf_len = r.buf_len;
     a.n_end = r.n_end;
     a.w0 = r.w0;

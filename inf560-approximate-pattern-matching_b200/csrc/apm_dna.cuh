@@ -69,6 +69,7 @@ __host__ __device__ inline size_t dna_smem_bytes(int table_words, int H) {
 
 struct DnaArgs {
     const uint8_t *buf;            // device text; buf[0] is global byte buf_offset
+    const uint32_t *packed;        // optional resident 2-bit copy of buf (dna_pack_kernel): word w = symbols [16 w, 16 w + 16)
     long long buf_len, n_end;      // valid bytes; local index of the global end of text
     long long w0, w1;              // local window-start range of this round
     int q, k, mmax, table_words;
@@ -164,7 +165,10 @@ __device__ __forceinline__ void dna_probe(const DnaArgs &a, const uint32_t *slab
     }
 }
 
-template <int H>
+// PACKED: the text also exists as a resident 2-bit copy (apm_text_pack_device: searched repeatedly, packed once); the scan
+// then streams a quarter of the bytes and skips the packing -- 4-byte loads of ready-made slab words.  Only the first and
+// the last region of the text still pack from the raw bytes (their fringes need the bounds-checked loads).
+template <int H, bool PACKED = false>
 __global__ void __launch_bounds__(kDnaThreads, 1) dna_scan_kernel(const __grid_constant__ DnaArgs a) {
     extern __shared__ __align__(16) uint32_t s_mem[];
     __shared__ unsigned int s_count;
@@ -195,13 +199,25 @@ __global__ void __launch_bounds__(kDnaThreads, 1) dna_scan_kernel(const __grid_c
         for (long long tile = base0 + (long long)blockIdx.x * kTile; tile < t_end; tile += (long long)gridDim.x * kTile) {
             const long long base = tile + (long long)warp * REGION;  // first text position of this warp's region
             if (base >= t_end) continue;                             // warp-uniform
-            {   // the region this warp reads in the NEXT iteration: one 128-byte line per lane towards L2
+            if constexpr (PACKED) {  // the region this warp reads in the NEXT iteration: REGION / 4 bytes of packed words
+                const long long nb = base + (long long)gridDim.x * kTile;
+                if (lane < REGION / 512 && nb + REGION <= a.buf_len)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned char *>(a.packed + (nb >> 4)) + 128 * lane));
+            } else {  // one 128-byte line per lane towards L2
                 const long long nb = base + (long long)gridDim.x * kTile + 128ll * lane;
                 if (lane < REGION / 128 && nb + 128 <= a.buf_len) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.buf + nb));
             }
             // ---- load + pack: lane l takes the 16-byte chunks l, l + 32, ... (coalesced), one packed word each
             uint4 raw[2 * H];
-            if (base >= 16 && base + REGION + 32 <= a.buf_len) {  // warp-uniform: the region and both fringes exist
+            if (PACKED && base >= 16 && base + REGION + 32 <= a.buf_len) {  // warp-uniform; base is a multiple of 16
+                const uint32_t *src = a.packed + (base >> 4) + lane;
+                uint32_t pw[2 * H];
+#pragma unroll
+                for (int c = 0; c < 2 * H; ++c) pw[c] = __ldg(src + 32 * c);
+#pragma unroll
+                for (int c = 0; c < 2 * H; ++c) slab[1 + lane + 32 * c] = pw[c];
+                if (lane < 2) slab[lane ? 1 + 64 * H : 0] = __ldg(a.packed + (base >> 4) + (lane ? 64 * H : -1));
+            } else if (base >= 16 && base + REGION + 32 <= a.buf_len) {  // warp-uniform: the region and both fringes exist
                 const uint4 *src = reinterpret_cast<const uint4 *>(a.buf + base) + lane;
 #pragma unroll
                 for (int c = 0; c < 2 * H; ++c) raw[c] = __ldg(src + 32 * c);
@@ -272,6 +288,24 @@ __global__ void __launch_bounds__(kDnaThreads, 1) dna_scan_kernel(const __grid_c
     }
     __syncthreads();
     if (threadIdx.x == 0) a.seg_count[blockIdx.x] = min(s_count, a.seg_cap);
+}
+
+// 2-bit copy of a text buffer for repeated searches: out[w] = dna_pack16 of bytes [16 w, 16 w + 16) (bytes past the end
+// pack as code 0, like the scan's own bounds-checked loads).  nwords = ceil(len / 16) + 1 (one pad word).
+__global__ void __launch_bounds__(256) dna_pack_kernel(const uint8_t *__restrict__ buf, long long len, uint32_t *__restrict__ out,
+                                                        long long nwords) {
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (long long)gridDim.x * blockDim.x) {
+        const long long pos = 16 * w;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (pos + 16 <= len) {
+            v = __ldg(reinterpret_cast<const uint4 *>(buf + pos));
+        } else if (pos < len) {
+            uint32_t t[4] = {0u, 0u, 0u, 0u};
+            for (int i = 0; i < 16 && pos + i < len; ++i) t[i >> 2] |= (uint32_t)buf[pos + i] << (8 * (i & 3));
+            v = make_uint4(t[0], t[1], t[2], t[3]);
+        }
+        out[w] = dna_pack16(v);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

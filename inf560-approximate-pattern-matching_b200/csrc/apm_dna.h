@@ -31,6 +31,7 @@ struct DnaSet {
 // per-launch arguments that do not live in the DnaSet
 struct DnaRun {
     const uint8_t *buf;
+    const uint32_t *packed = nullptr;  // optional resident 2-bit copy of buf (dna_pack_text); buf must be 16-byte aligned
     long long buf_len, n_end, w0, w1;
     int k;
     const int *fp_id, *fp_m;
@@ -50,6 +51,10 @@ __attribute__((visibility("hidden"))) bool dna_choose(const std::vector<std::str
 __attribute__((visibility("hidden"))) int dna_build(const std::vector<std::string> &pats, const std::vector<int> &ids, int k, int q,
                                                   int h, int nseg, size_t cand_bytes, DnaSet *out);
 __attribute__((visibility("hidden"))) void dna_free(DnaSet *s);
+// 2-bit copy of a device text buffer (16-byte aligned) for repeated searches: words needed, and the packing itself
+__attribute__((visibility("hidden"))) unsigned long long dna_pack_words(unsigned long long buf_len);
+__attribute__((visibility("hidden"))) cudaError_t dna_pack_text(const uint8_t *d_buf, unsigned long long buf_len, uint32_t *d_packed,
+                                                                cudaStream_t st);
 // scan + verification of one round on `st` (stream ordered).  *launches += kernels launched.
 __attribute__((visibility("hidden"))) cudaError_t dna_launch(const DnaSet &s, const DnaRun &r, cudaStream_t st, int *launches);
 

@@ -173,3 +173,88 @@ def test_tiny_texts():
     for text, pats, k in ((b"ACGTACGT", [b"ACGTACGT"], 0), (b"ACGTACGTA", [b"ACGTACGT"], 0), (b"ACGTACG", [b"ACGTACGT"], 0),
                           (b"A" * 40, [b"A" * 16, b"A" * 17], 1), (b"ACGTACGTACGTACGTACGT", [b"CGTACGTACGTACGTA"], 1)):
         assert apm_b200.count_matches(text, pats, k) == oracle.count_matches(text, pats, k), (text, pats, k)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# resident 2-bit copy of the text (apm_text_pack_device / apm_plan_count_device_packed)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,P,m,k", [(3_000_001, 64, 64, 4), (777_777, 16, 32, 2), (1_234_567, 8, 200, 10), (70_000, 5, 50, 0),
+                                     (4099, 3, 40, 1)])
+def test_packed_text_counts_equal_plain(n, P, m, k):
+    """every probe-stride class; text lengths that are not multiples of 16 or of the scan's regions; sub-ranges of window
+    starts; a text with bytes outside ACGT (they alias in the 2-bit code, the byte-exact stage decides)"""
+    import torch
+    rng = np.random.default_rng(n + m)
+    base = bytearray(oracle.synth_text(0x5EED0001, 3 * n, n).tobytes())
+    for pos in rng.integers(0, n, size=n // 5000):  # sprinkle newlines / N / lower case
+        base[int(pos)] = int(rng.choice(list(b"\nNacgt")))
+    pats = []
+    for i in range(P):
+        off = int(rng.integers(0, n - m))
+        p = bytearray(bytes(base[off:off + m]).upper().replace(b"\n", b"A").replace(b"N", b"C"))
+        for s_ in range(i % (k + 2)):
+            p[int(rng.integers(0, m))] = ord("ACGT"[int(rng.integers(0, 4))])
+        pats.append(bytes(p))
+    pats.append(bytes(base[-m:]).upper().replace(b"\n", b"A").replace(b"N", b"C"))
+    text = torch.frombuffer(base, dtype=torch.uint8).cuda()
+    pk = torch.empty(apm_b200.text_pack_bytes(n), dtype=torch.uint8, device="cuda")
+    apm_b200.text_pack_device(text.data_ptr(), n, pk.data_ptr())
+    torch.cuda.synchronize()
+    # the packed words themselves: word w = codes of bytes [16 w, 16 w + 16)
+    words = pk.cpu().numpy().view(np.uint32)
+    arr = np.frombuffer(bytes(base), dtype=np.uint8)
+    for w in (0, 1, (n // 16) // 2, n // 16 - 1, (n + 15) // 16 - 1):
+        chunk = arr[16 * w: 16 * w + 16]
+        want = sum(((int(c) >> 1) & 3) << (2 * i) for i, c in enumerate(chunk))
+        assert int(words[w]) == want, w
+    with apm_b200.Plan(pats, k) as plan:
+        before = apm_b200.launch_count()
+        plan.count_device(text.data_ptr(), 0, n, n, 0, n)
+        plain = plan.read_counts()
+        assert apm_b200.launch_count() > before
+        plan.zero_counts()
+        plan.count_device_packed(text.data_ptr(), pk.data_ptr(), 0, n, n, 0, n)
+        assert plan.read_counts() == plain
+        # window sub-ranges through the packed path add up to the whole
+        plan.zero_counts()
+        cuts = [0, n // 3 + 5, n // 2, n - m, n]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            plan.count_device_packed(text.data_ptr(), pk.data_ptr(), 0, n, n, a, b)
+        assert plan.read_counts() == plain
+        # d_packed = NULL is the plain call
+        plan.zero_counts()
+        plan.count_device_packed(text.data_ptr(), 0, 0, n, n, 0, n)
+        assert plan.read_counts() == plain
+    if n <= 100_000:
+        assert plain == oracle.count_matches(bytes(base), pats, k)
+
+
+def test_packed_text_shard_view_and_errors():
+    """a database shard: the packed copy belongs to the shard's own buffer (global offset b0 > 0); misaligned buffers
+    are refused"""
+    import torch
+    n, m, k = 2_000_000, 64, 4
+    raw = oracle.synth_text(0x5EED0001, 99, n).tobytes()
+    rng = np.random.default_rng(5)
+    pats = [raw[o:o + m] for o in (int(x) for x in rng.integers(0, n - m, size=12))]
+    text = torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
+    with apm_b200.Plan(pats, k) as plan:
+        plan.count_device(text.data_ptr(), 0, n, n, 0, n)
+        whole = plan.read_counts()
+        plan.zero_counts()
+        W = n - k
+        cuts = [(W * g // 3) & ~15 for g in range(3)] + [W]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            e = min(n, b + m - 1)
+            view = text[a:e]                       # a is a multiple of 16: the view is 16-byte aligned
+            pk = torch.empty(apm_b200.text_pack_bytes(e - a), dtype=torch.uint8, device="cuda")
+            apm_b200.text_pack_device(view.data_ptr(), e - a, pk.data_ptr())
+            plan.count_device_packed(view.data_ptr(), pk.data_ptr(), a, e - a, n, a, b)
+        assert plan.read_counts() == whole
+        pk = torch.empty(apm_b200.text_pack_bytes(n), dtype=torch.uint8, device="cuda")
+        with pytest.raises(apm_b200.ApmError) as ei:
+            apm_b200.text_pack_device(text.data_ptr() + 4, n - 4, pk.data_ptr())
+        assert ei.value.code == apm_b200.APM_EINVAL
+        with pytest.raises(apm_b200.ApmError) as ei:
+            plan.count_device_packed(text.data_ptr() + 4, pk.data_ptr(), 4, n - 4, n, 4, n)
+        assert ei.value.code == apm_b200.APM_EINVAL
