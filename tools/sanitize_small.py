@@ -54,6 +54,26 @@ for mode in ("direct", "band", "filter"):
         got = plan.read_counts()
     ok &= got == want
     print("shards", mode, "ok" if got == want else f"MISMATCH {got} {want}")
+# round 2 (late): automatic routing -- m = 32 only (two-row sweep), m = 64 only, 65..224 and longer lists -- and the
+# resident 2-bit text copy
+apm_b200.set_option("mode", "direct"); apm_b200.set_option("cell", "auto")
+for pset in ([text[i:i + 32] for i in (10, 500, 7000)], [text[i:i + 64] for i in (10, 500, 7000)],
+             [text[100:200], text[300:524], text[600:825], text[-40:] + b"ACGT" * 10]):
+    got = apm_b200.count_matches(text, pset, 2)
+    w3 = oracle.count_matches(text, pset, 2)
+    ok &= got == w3
+    print("auto routing", [len(p) for p in pset], "ok" if got == w3 else f"MISMATCH {got} {w3}")
+apm_b200.set_option("mode", "filter")
+dtext = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+pk = torch.empty(apm_b200.text_pack_bytes(len(text)), dtype=torch.uint8, device="cuda")
+apm_b200.text_pack_device(dtext.data_ptr(), len(text), pk.data_ptr())
+with apm_b200.Plan(pats2, 1) as plan:
+    plan.count_device_packed(dtext.data_ptr(), pk.data_ptr(), 0, len(text), len(text), 0, len(text))
+    got = plan.read_counts()
+w4 = oracle.count_matches(text, pats2, 1)
+ok &= got == w4
+print("packed text", "ok" if got == w4 else f"MISMATCH {got} {w4}")
+apm_b200.set_option("mode", "direct")
 # filter mode with an overflowing candidate buffer (fallback to the band kernel) on low-complexity text
 apm_b200.set_option("mode", "filter"); apm_b200.set_option("filter_cand_mb", "1")
 lc = b"A" * 200000
