@@ -216,6 +216,38 @@ def run_config_1gib(torch, apm_b200, dev, stream, name: str, P: int, m: int, k: 
 
 
 
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE configs 1 and 2: the reference's own CPU-runnable cases on dna/small_chrY_x100.fa (committed as
+# tests/golden/fixtures.npz with the outputs of the reference's apm_sequential, tests/golden/golden.json).
+# Launch-bound jobs: per-call latency through the one-shot C-ABI call with host buffers, counts against the goldens.
+# ---------------------------------------------------------------------------------------------------
+def run_configs_small(apm_b200) -> dict:
+    sys.path.insert(0, ROOT)
+    from tests.golden_util import cases, fixtures
+    fx = fixtures()
+    out = {}
+    for key, name in (("1", "config1_readme"), ("2", "config2")):
+        c = next(x for x in cases() if x["name"] == name)
+        text = fx[c["text"]]
+        res = {"workload": f"{name}: dna/{c['text']}.fa ({len(text)} B), {len(c['patterns'])} patterns "
+                           f"m={sorted(set(len(p) for p in c['patterns']))}, k={c['k']}",
+               "cells": float(sum(cells_text(len(text), 1, len(p), c["k"]) for p in c["patterns"]))}
+        for mode in ("direct", "filter"):
+            apm_b200.set_option("mode", mode)
+            ts = []
+            got = None
+            for i in range(12):
+                t0 = time.perf_counter()
+                got = apm_b200.count_matches(text, c["patterns"], c["k"])
+                ts.append(time.perf_counter() - t0)
+            ms = sorted(ts[2:])[len(ts[2:]) // 2] * 1e3
+            res[mode] = {"ms_per_call": ms, "gcups": res["cells"] / (ms * 1e-3) / 1e9,
+                         "equals_reference_golden": got == c["expected"]}
+        apm_b200.set_option("mode", "direct")
+        out[key] = res
+    return out
+
 # ---------------------------------------------------------------------------------------------------
 # End to end with the INGEST inside the timed region: config 3 (1 GiB) in exact filter mode, where
 # the search itself is 0.4 ms, through the one-shot C-ABI calls a user makes -- host buffer (pinned / pageable) and file
@@ -620,8 +652,9 @@ def run_ours(args) -> None:
         del shard
         torch.cuda.empty_cache()
         apm_b200.release_cache()
-        configs = {"3": run_config_1gib(torch, apm_b200, dev, stream, "config3", 1024, 64, 4, 7, hbm_peak),
-                   "4": run_config_1gib(torch, apm_b200, dev, stream, "config4", 256, 200, 10, 14, hbm_peak)}
+        configs = run_configs_small(apm_b200)
+        configs["3"] = run_config_1gib(torch, apm_b200, dev, stream, "config3", 1024, 64, 4, 7, hbm_peak)
+        configs["4"] = run_config_1gib(torch, apm_b200, dev, stream, "config4", 256, 200, 10, 14, hbm_peak)
         ingest = run_ingest_e2e(torch, apm_b200, dev)
 
     line = {
