@@ -842,7 +842,7 @@ int launch_sliced(apm_plan *pl, SlicedList &l, const uint8_t *d_buf, long long b
         return launch_band(pl, l, a, lim - w0, st);
     // auto (measured on B200, profiles/r02_cell_reuse_*.jsonl): the register-file bound of the co-issued cell decides.
     // CELL 3 (4 LOP3 + 3 IMAD ordered for the operand reuse cache) wins for every list that runs at 3 CTAs per SM
-    // (m <= 224): m = 64 120.5 TCUPS (CELL 1: 114.2), m = 128 116.6 (CELL 0: 109.3), ragged single blocks m = 50 113.0
+    // (m <= 224 with the 4-symbol DNA alphabet): m = 64 120.5 TCUPS (CELL 1: 114.2), m = 128 116.6 (CELL 0: 109.3), ragged single blocks m = 50 113.0
     // (CELL 1: 102.7); for longer patterns (2 CTAs per SM) plain LOP3 stays ahead (m = 1000: 91.8 vs 86.4).  m = 32:
     // CELL 3 in the two-row sweep (114.9; CELL 2 one row: 110.6); ragged m < 32: CELL 2 (CELL 3 is within +-2 %).
     if (pl->opt.cell < 0) {
@@ -852,7 +852,14 @@ int launch_sliced(apm_plan *pl, SlicedList &l, const uint8_t *d_buf, long long b
             return launch_sliced_mc<32, 2>(pl, l, a, lim - w0, st);
         }
         if (l.ragged == 1) return launch_sliced_mc<64, 3, 1>(pl, l, a, lim - w0, st);
-        return l.mmax <= kSlicedThreeCtaLen ? launch_sliced_mc<64, 3>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 0>(pl, l, a, lim - w0, st);
+        // CTAs per SM of this list (registers allow three; the U table grows with the pattern length and the number of
+        // symbol planes).  The longer row recurrence of CELL 3 needs the other warps of the scheduler to hide it: with
+        // one CTA per SM (8 symbols) plain LOP3 is 8-15 % ahead, with two only single-block patterns keep CELL 3
+        // (tools/alphabet_bench.py: 5 symbols m = 64 115.1 vs 103.5, m = 128 106.9 vs 108.0; 8 symbols 90.6 vs 97.7).
+        const size_t cta_smem = sliced_smem_bytes(pl->nplanes, sliced_rowsU(l.mmax)) + 1024;
+        const int ctas = (int)std::min<size_t>(3, ((size_t)pl->smem_optin + 1024) / cta_smem);
+        const bool cell3 = ctas >= 3 || (ctas == 2 && l.mmax <= 64);
+        return cell3 ? launch_sliced_mc<64, 3>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 0>(pl, l, a, lim - w0, st);
     }
     switch (pl->opt.cell) {
         case 3: return l.MC == 32 ? launch_sliced_mc<32, 3>(pl, l, a, lim - w0, st) : launch_sliced_mc<64, 3>(pl, l, a, lim - w0, st);

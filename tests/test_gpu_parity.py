@@ -878,3 +878,24 @@ def test_all_m32_and_all_m64_sets():
                 pats.append(bytes(p))
             for k in (0, 2, 4):
                 assert apm_b200.count_matches(text, pats, k) == oracle.count_matches(text, pats, k), (n, m, k)
+
+
+@pytest.mark.parametrize("alphabet", [b"ACGTN", b"ACGTNMRY"])
+def test_auto_routing_larger_alphabets(alphabet):
+    """5 and 8 symbol planes: the U table leaves two / one CTA per SM, where the automatic cell choice falls back to
+    plain LOP3 for multi-block (two CTAs) or all 64-column lists (one CTA); every list class against the oracle"""
+    apm_b200.set_option("kernel", "sliced")
+    rng = np.random.default_rng(len(alphabet))
+    n = 120_000
+    arr = np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), size=n)]
+    text = arr.tobytes()
+    pats = []
+    for m in (32, 32, 64, 64, 20, 50, 63, 65, 128, 200, 224, 225, 300):
+        off = int(rng.integers(0, n - m))
+        p = bytearray(text[off:off + m])
+        for s_ in range(int(rng.integers(0, 4))):
+            p[int(rng.integers(0, m))] = alphabet[int(rng.integers(0, len(alphabet)))]
+        pats.append(bytes(p))
+    pats.append(text[-50:] + alphabet[:4] * 3)
+    for k in (0, 3):
+        assert apm_b200.count_matches(text, pats, k) == oracle.count_matches(text, pats, k), k
