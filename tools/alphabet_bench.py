@@ -1,5 +1,9 @@
+#!/usr/bin/env python
+"""Exploration bench: direct-mode slab rate of every DP-cell code for texts over 4, 5 and 8 symbols (the U table of the
+sliced kernel grows with the number of symbol planes: three, two, one CTA per SM) -- the data behind the automatic cell
+choice by occupancy (profiles/r02_alphabet_bench.txt)."""
 import sys, os, json
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "inf560-approximate-pattern-matching_b200"))
 import torch, numpy as np, apm_b200
 n = 64 << 20
